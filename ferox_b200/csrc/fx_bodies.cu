@@ -1,0 +1,183 @@
+// fx_bodies.cu -- per-body kernels (K10), step bookkeeping and the single-item entry points that back
+// the public per-body / per-pair functions of ferox.h.
+//
+// k_integrate_position replaces reference src/world.c:251-252 + :481-482: frIntegrateForBodyPosition
+// (src/rigid_body.c:433-443) -> frSetBodyAngle (:225-238: normalise into [pi, 3*pi), sinf, cosf) ->
+// frGetShapeAABB (src/geometry.c:183-216), fused with the force clear of frPostStepWorld.
+// 116 B read + 56 B written per body (+ polygon vertices).
+#include "fx_device.h"
+#include "fx_kernels.h"
+#include "fx_narrow.cuh"
+#include "fx_solver.cuh"
+
+#define BD_BLOCK 256
+
+__device__ __forceinline__ float4 shape_aabb(const ShapeDev *s, Xf t) {
+    if (s == nullptr) return make_float4(0.f, 0.f, 0.f, 0.f);
+    if (s->type == FX_SHAPE_CIRCLE) {
+        float r = s->radius;
+        return make_float4(t.p.x - r, t.p.y - r, 2.0f * r, 2.0f * r);
+    }
+    if (s->type == FX_SHAPE_POLYGON) {
+        float lox = FLT_MAX, loy = FLT_MAX, hix = -FLT_MAX, hiy = -FLT_MAX;
+        const int nv = s->nv;
+        for (int k = 0; k < nv; ++k) {
+            V2 v = xf_apply(s->verts[k], t);
+            if (lox > v.x) lox = v.x;
+            if (loy > v.y) loy = v.y;
+            if (hix < v.x) hix = v.x;
+            if (hiy < v.y) hiy = v.y;
+        }
+        return make_float4(lox, loy, hix - lox, hiy - loy);
+    }
+    return make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+__device__ __forceinline__ void integrate_position_one(const DevWorld &w, int i, float dt) {
+    const int type = __float_as_int(w.mprop[i].w) & 0xff;
+    if (type != FX_BODY_STATIC && dt > 0.0f) {
+        float4 pr = w.posrot[i];
+        const float4 v = w.vel[i];
+        pr.x += v.x * dt;
+        pr.y += v.y * dt;
+        if (v.z != 0.0f) {
+            const float old = w.angle[i];
+            const float target = old + (v.z * dt);
+            if (old != target) {                       // frSetBodyAngle early-out, rigid_body.c:226
+                const float a = fx_normalize_angle(target);
+                SinCos sc = fx_sincosf(a);
+                w.angle[i] = a;
+                pr.z = sc.s;
+                pr.w = sc.c;
+            }
+        }
+        w.posrot[i] = pr;
+        const int si = w.shape[i].x;
+        Xf t;
+        t.p = v2(pr.x, pr.y); t.sn = pr.z; t.cs = pr.w;
+        w.aabb[i] = shape_aabb(si >= 0 ? &w.shapes[si] : nullptr, t);
+    }
+}
+
+__global__ void __launch_bounds__(BD_BLOCK) k_integrate_position(DevWorld w) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
+        integrate_position_one(w, i, w.dt);
+        w.force[i] = make_float4(0.f, 0.f, 0.f, 0.f);    // frClearBodyForces, world.c:481-482
+    }
+}
+
+__global__ void k_begin_step(DevWorld w) {
+    StepCountersDev *c = w.ctr;
+    c->n_entries = c->n_cand = c->n_hits = c->n_manifolds = c->n_contacts = c->n_colors = 0u;
+    c->overflow = 0u;
+    c->sort_passes = 0u;
+    c->cell_min_x = c->cell_min_y = 0x7fffffff;
+    c->cell_max_x = c->cell_max_y = (int) 0x80000000;
+    c->grid_w = c->grid_h = 1u;
+    c->key_bits = 0u;
+    c->n_large = 0u;
+    c->uncolored = 0u;
+}
+
+__global__ void k_finish_step(DevWorld w, StepCountersDev *snapshot) {
+    *w.prev_count = w.ctr->n_manifolds;
+    *w.cur_flip ^= 1;
+    *snapshot = *w.ctr;
+}
+
+static inline int grid_for(long long n, int block, int max_blocks) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int) g;
+}
+
+void fx_launch_begin_step(const DevWorld &w, const FxLaunchCtx &cx) {
+    cudaMemsetAsync(cx.zero_base, 0, cx.zero_bytes, cx.stream);
+    k_begin_step<<<1, 1, 0, cx.stream>>>(w);
+}
+
+void fx_launch_integrate_position(const DevWorld &w, const FxLaunchCtx &cx) {
+    if (w.n == 0) return;
+    k_integrate_position<<<grid_for(w.n, BD_BLOCK, cx.max_blocks), BD_BLOCK, 0, cx.stream>>>(w);
+}
+
+void fx_launch_finish_step(const DevWorld &w, const FxLaunchCtx &cx, StepCountersDev *snapshot) {
+    k_finish_step<<<1, 1, 0, cx.stream>>>(w, snapshot);
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-item entry points
+// ---------------------------------------------------------------------------------------------
+
+// frIntegrateForBodyVelocity / frIntegrateForBodyPosition on one body of a (scratch) world
+__global__ void k_single_body(DevWorld w, int i, int op, float dt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (op == 0) {
+        float4 v = w.vel[i];
+        const float4 mp = w.mprop[i], f = w.force[i];
+        if (v.w > 0.0f && dt > 0.0f) {                  // src/rigid_body.c:418-427 (no gravity here)
+            float s = v.w * dt;
+            v.x = v.x + f.x * s;
+            v.y = v.y + f.y * s;
+            v.z += (f.z * mp.y) * dt;
+            w.vel[i] = v;
+        }
+    } else {
+        integrate_position_one(w, i, dt);
+    }
+}
+
+// frApplyAccumulatedImpulses (op 0) / frResolveCollision (op 1) on bodies 0 and 1 of a scratch world
+__global__ void k_single_pair_solve(DevWorld w, CollisionPod *col, int op, float inv_dt) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    float4 va4 = w.vel[0], vb4 = w.vel[1];
+    const float inv_ma = va4.w, inv_mb = vb4.w, inv_ia = w.mprop[0].y, inv_ib = w.mprop[1].y;
+    if (inv_ma + inv_mb <= 0.0f) {
+        if (op == 0) {
+            if ((__float_as_int(w.mprop[0].w) & 0xff) == FX_BODY_STATIC) w.vel[0] = make_float4(0.f, 0.f, 0.f, va4.w);
+            if ((__float_as_int(w.mprop[1].w) & 0xff) == FX_BODY_STATIC) w.vel[1] = make_float4(0.f, 0.f, 0.f, vb4.w);
+        }
+        return;
+    }
+    if (op == 1 && inv_dt <= 0.0f) return;
+    const float4 pa4 = w.posrot[0], pb4 = w.posrot[1];
+    const V2 n = col->direction, t = vperp_right(n);
+    Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
+    for (int c = 0; c < col->count && c < 2; ++c) {
+        ContactPod &ct = col->contacts[c];
+        ContactK k;
+        contact_arms(k, ct.point, v2(pa4.x, pa4.y), v2(pb4.x, pb4.y));
+        if (op == 0) {
+            contact_masses(k, n, t, inv_ma, inv_mb, inv_ia, inv_ib);
+            ct.normalMass = k.nmass;
+            ct.tangentMass = k.tmass;
+            contact_warm_start(k, n, t, ct.normalScalar, ct.tangentScalar, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
+        } else {
+            k.bias = contact_bias(ct.depth, inv_dt);
+            k.nmass = ct.normalMass;
+            k.tmass = ct.tangentMass;
+            contact_resolve(k, n, t, col->friction, col->restitution, ct.normalScalar, ct.tangentScalar, inv_ma, inv_mb,
+                            inv_ia, inv_ib, va, vb);
+        }
+    }
+    w.vel[0] = make_float4(va.x, va.y, va.w, inv_ma);
+    w.vel[1] = make_float4(vb.x, vb.y, vb.w, inv_mb);
+}
+
+__global__ void k_sincos(const float *a, int n, float *s, float *c) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        SinCos r = fx_sincosf(a[i]);
+        s[i] = r.s;
+        c[i] = r.c;
+    }
+}
+
+void fx_launch_single_body(const DevWorld &w, cudaStream_t s, int i, int op, float dt) { k_single_body<<<1, 32, 0, s>>>(w, i, op, dt); }
+void fx_launch_single_pair_solve(const DevWorld &w, cudaStream_t s, CollisionPod *col, int op, float inv_dt) {
+    k_single_pair_solve<<<1, 32, 0, s>>>(w, col, op, inv_dt);
+}
+void fx_launch_sincos(const float *a, int n, float *s, float *c, cudaStream_t st) {
+    if (n <= 0) return;
+    k_sincos<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(a, n, s, c);
+}

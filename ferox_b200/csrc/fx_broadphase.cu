@@ -1,0 +1,445 @@
+// fx_broadphase.cu -- sort-based spatial hash (kernels K1-K4 of SURVEY.md section 2.2).
+//
+// Replaces reference src/world.c:432-444 + src/broad_phase.c:99-179 (insert every body into a hash of
+// cells, then query every body and de-duplicate) and, fused into the first pass, the velocity
+// integration of src/world.c:216-220.  The candidate rule is the reference's, exactly: bodies i < j
+// are candidates iff their inclusive, truncated-toward-zero cell rectangles intersect and
+// invMass(i) + invMass(j) > 0 -- there is no AABB test.
+//
+// Stages (all sizes live on the device; no host round trip inside a step):
+//   k_body_prepass   per body: [gravity + velocity integration], cell rectangle, cells covered,
+//                    world cell bounds (atomics), exclusive offsets via decoupled look-back scan
+//   k_plan           1 thread: dense key geometry (grid_w/h, key bits, radix passes)
+//   k_emit_entries   per body: (cellKey, packedBody) for every covered cell; bodies covering more
+//   k_emit_large     than FX_LARGE_CELLS cells are expanded by a whole block each (e.g. a ground
+//                    plane spanning thousands of cells)
+//   k_sort_hist + k_sort_pass (x passes)  onesweep-style LSD radix sort, 8-bit digits, one kernel
+//                    per digit with chained-scan look-back per digit; stable, deterministic
+//   k_emit_pairs     per sorted entry: walk the rest of its cell run; a pair is emitted only in its
+//                    canonical cell (the min-corner of the rectangle intersection), which removes
+//                    duplicates without a hash set; ordered append via look-back
+// HBM bytes per step (algorithmic): prepass 68 N, emit 16 N + 8 K, sort (8+8) K per pass + 4 K
+// histogram, pair emission 8 K + 8 C.
+#include "fx_device.h"
+#include "fx_kernels.h"
+#include "fx_scan.cuh"
+
+#define BP_BLOCK 256
+#define FX_LARGE_CELLS 32u
+#define FX_MAX_CELLS_PER_BODY (1u << 24)
+
+#define SORT_ITEMS 8
+#define SORT_TILE (BP_BLOCK * SORT_ITEMS)
+
+// packed entry value: [28:0] body index, 29: entry is in the body's min-x column, 30: min-y row,
+// 31: body has invMass > 0
+#define ENT_BODY(v) ((v) & 0x1fffffffu)
+#define ENT_X0 (1u << 29)
+#define ENT_Y0 (1u << 30)
+#define ENT_MASS (1u << 31)
+
+struct CellRect {
+    int x0, y0, x1, y1;
+};
+
+__device__ __forceinline__ CellRect body_rect(float4 a, float inv_cell) {
+    CellRect r;
+    r.x0 = cell_coord(a.x, inv_cell);
+    r.y0 = cell_coord(a.y, inv_cell);
+    r.x1 = cell_coord(a.x + a.z, inv_cell);
+    r.y1 = cell_coord(a.y + a.w, inv_cell);
+    return r;
+}
+
+__device__ __forceinline__ unsigned int rect_cells(CellRect r, bool *bad) {
+    *bad = false;
+    if (r.x1 < r.x0 || r.y1 < r.y0) return 0u;
+    unsigned long long w = (unsigned long long) ((long long) r.x1 - r.x0 + 1);
+    unsigned long long h = (unsigned long long) ((long long) r.y1 - r.y0 + 1);
+    unsigned long long c = w * h;
+    if (c > FX_MAX_CELLS_PER_BODY) { *bad = true; return 0u; }
+    return (unsigned int) c;
+}
+
+// gravity + velocity integration, reference src/rigid_body.c:309-316 and 418-427 (called from
+// src/world.c:216-220).  The force accumulator is consumed here and cleared by the position pass.
+__device__ __forceinline__ float4 integrate_velocity(float4 v, float4 mp, float4 f, float gx, float gy, float dt) {
+    float mass = mp.x, inv_inertia = mp.y, gscale = mp.z, inv_mass = v.w;
+    if (mass > 0.0f) {
+        float k = gscale * mass;
+        f.x = f.x + gx * k;
+        f.y = f.y + gy * k;
+    }
+    if (inv_mass > 0.0f && dt > 0.0f) {
+        float s = inv_mass * dt;
+        v.x = v.x + f.x * s;
+        v.y = v.y + f.y * s;
+        v.z += (f.z * inv_inertia) * dt;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(BP_BLOCK) k_integrate_velocity(DevWorld w) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x)
+        w.vel[i] = integrate_velocity(w.vel[i], w.mprop[i], w.force[i], w.gx, w.gy, w.dt);
+}
+
+__global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_velocity, unsigned long long *status,
+                                                           unsigned int *ticket) {
+    __shared__ int s_b[4];
+    const int ntiles = (w.n + BP_BLOCK - 1) / BP_BLOCK;
+    for (;;) {
+        unsigned int tile = claim_tile(ticket);
+        if ((int) tile >= ntiles) return;
+        int i = (int) tile * BP_BLOCK + (int) threadIdx.x;
+        unsigned int cnt = 0u;
+        CellRect r = { 0x7fffffff, 0x7fffffff, (int) 0x80000000, (int) 0x80000000 };
+        bool valid = i < w.n;
+        if (valid) {
+            if (fuse_velocity)
+                w.vel[i] = integrate_velocity(w.vel[i], w.mprop[i], w.force[i], w.gx, w.gy, w.dt);
+            CellRect rr = body_rect(w.aabb[i], w.inv_cell);
+            bool bad;
+            cnt = rect_cells(rr, &bad);
+            if (bad) atomicOr(&w.ctr->overflow, 16u);
+            if (cnt) r = rr;
+            if (cnt > FX_LARGE_CELLS) {
+                unsigned int slot = atomicAdd(&w.ctr->n_large, 1u);
+                if (slot < w.cap_large) w.large_list[slot] = (unsigned int) i;
+            }
+        }
+        // world cell bounds: warp shuffles, then one atomic per warp
+        int mnx = r.x0, mny = r.y0, mxx = r.x1, mxy = r.y1;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            mnx = min(mnx, __shfl_xor_sync(0xffffffffu, mnx, d));
+            mny = min(mny, __shfl_xor_sync(0xffffffffu, mny, d));
+            mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
+            mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
+        }
+        if (lane_id() == 0 && mnx <= mxx) {
+            atomicMin(&w.ctr->cell_min_x, mnx);
+            atomicMin(&w.ctr->cell_min_y, mny);
+            atomicMax(&w.ctr->cell_max_x, mxx);
+            atomicMax(&w.ctr->cell_max_y, mxy);
+        }
+        unsigned int total;
+        unsigned int excl = block_exclusive_scan<BP_BLOCK>(cnt, &total);
+        unsigned int base = tile_exclusive_prefix(status, tile, total);
+        if (valid) {
+            w.cell_cnt[i] = cnt;
+            w.cell_off[i] = base + excl;
+        }
+        if ((int) tile == ntiles - 1 && threadIdx.x == 0) w.ctr->n_entries = base + total;
+        (void) s_b;
+    }
+}
+
+__global__ void k_plan(DevWorld w) {
+    StepCountersDev *c = w.ctr;
+    if (c->n_entries > w.cap_entries) {
+        c->overflow |= 1u;
+        c->n_entries = w.cap_entries;
+    }
+    if (c->n_large > w.cap_large) { c->overflow |= 1u; c->n_large = w.cap_large; }
+    unsigned long long gw = 1, gh = 1;
+    if (c->cell_min_x <= c->cell_max_x) {
+        gw = (unsigned long long) ((long long) c->cell_max_x - c->cell_min_x + 1);
+        gh = (unsigned long long) ((long long) c->cell_max_y - c->cell_min_y + 1);
+    }
+    unsigned long long cells = gw * gh;
+    if (gw > 0xffffffffull || gh > 0xffffffffull || cells > 0x100000000ull) {
+        // the dense key does not fit 32 bits: refuse loudly (host reports it), emit nothing
+        c->overflow |= 16u;
+        c->n_entries = 0;
+        gw = gh = 1;
+        cells = 1;
+    }
+    c->grid_w = (unsigned int) gw;
+    c->grid_h = (unsigned int) gh;
+    unsigned int bits = 1;
+    while (bits < 32 && (1ull << bits) < cells) ++bits;
+    c->key_bits = bits;
+    c->sort_passes = (bits + 7) / 8;
+}
+
+__device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, int x, int y, const CellRect &r,
+                                           unsigned int body, unsigned int massbit, int minx, int miny,
+                                           unsigned int gw) {
+    if (pos >= w.cap_entries) return;
+    unsigned int key = (unsigned int) (y - miny) * gw + (unsigned int) (x - minx);
+    unsigned int v = body | massbit | (x == r.x0 ? ENT_X0 : 0u) | (y == r.y0 ? ENT_Y0 : 0u);
+    w.keys[0][pos] = key;
+    w.vals[0][pos] = v;
+}
+
+__global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w) {
+    const int minx = w.ctr->cell_min_x, miny = w.ctr->cell_min_y;
+    const unsigned int gw = w.ctr->grid_w;
+    if (w.ctr->overflow & 16u) return;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
+        unsigned int cnt = w.cell_cnt[i];
+        if (cnt == 0u || cnt > FX_LARGE_CELLS) continue;
+        CellRect r = body_rect(w.aabb[i], w.inv_cell);
+        unsigned int pos = w.cell_off[i];
+        unsigned int massbit = (w.vel[i].w > 0.0f) ? ENT_MASS : 0u;
+        for (int y = r.y0; y <= r.y1; ++y)
+            for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw);
+    }
+}
+
+__global__ void __launch_bounds__(BP_BLOCK) k_emit_large(DevWorld w) {
+    const int minx = w.ctr->cell_min_x, miny = w.ctr->cell_min_y;
+    const unsigned int gw = w.ctr->grid_w;
+    if (w.ctr->overflow & 16u) return;
+    const unsigned int nl = w.ctr->n_large;
+    for (unsigned int l = blockIdx.x; l < nl; l += gridDim.x) {
+        unsigned int i = w.large_list[l];
+        CellRect r = body_rect(w.aabb[i], w.inv_cell);
+        unsigned int rw = (unsigned int) (r.x1 - r.x0 + 1);
+        unsigned int cnt = w.cell_cnt[i], pos = w.cell_off[i];
+        unsigned int massbit = (w.vel[i].w > 0.0f) ? ENT_MASS : 0u;
+        for (unsigned int t = threadIdx.x; t < cnt; t += blockDim.x)
+            emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// radix sort of (key, value) entries
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BP_BLOCK) k_sort_hist(SortJob job) {
+    __shared__ unsigned int s_h[4][256];
+    const unsigned int n = *job.n;
+    const unsigned int passes = job.passes_dev ? *job.passes_dev : job.passes;
+    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) (&s_h[0][0])[t] = 0u;
+    __syncthreads();
+    const unsigned int *keys = job.keys[0];
+    for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+        unsigned int k = keys[e];
+        for (unsigned int p = 0; p < passes; ++p) atomicAdd(&s_h[p][(k >> (8 * p)) & 255u], 1u);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) {
+        unsigned int v = (&s_h[0][0])[t];
+        if (v) atomicAdd(&job.ghist[t], v);
+    }
+}
+
+// per-digit tile status: [31:30] flag, [29:0] count
+#define DS_AGG (1u << 30)
+#define DS_PFX (2u << 30)
+#define DS_VAL ((1u << 30) - 1u)
+
+__global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
+    __shared__ unsigned int s_wc[BP_BLOCK / 32][256];   // per-warp digit counters -> exclusive bases
+    __shared__ unsigned int s_gb[256];                  // global base per digit for this tile
+    const unsigned int n = *job.n;
+    const unsigned int passes = job.passes_dev ? *job.passes_dev : job.passes;
+    if ((unsigned int) pass >= passes) return;
+    const unsigned int *kin = job.keys[pass & 1], *vin = job.vals[pass & 1];
+    unsigned int *kout = job.keys[(pass + 1) & 1], *vout = job.vals[(pass + 1) & 1];
+    unsigned int *dstatus = job.dstatus + (size_t) pass * job.dstatus_stride;
+    unsigned int *ticket = job.tickets + pass;
+    const unsigned int shift = 8u * (unsigned int) pass;
+    const unsigned int ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const unsigned int warp = threadIdx.x >> 5, lane = lane_id();
+
+    // exclusive scan of the global digit histogram of this pass (256 bins = 256 threads)
+    unsigned int tot;
+    const unsigned int bin_base = block_exclusive_scan<BP_BLOCK>(job.ghist[pass * 256 + threadIdx.x], &tot);
+
+    for (;;) {
+        unsigned int tile = claim_tile(ticket);
+        if (tile >= ntiles) return;
+        for (int t = threadIdx.x; t < (BP_BLOCK / 32) * 256; t += blockDim.x) (&s_wc[0][0])[t] = 0u;
+        __syncthreads();
+        unsigned int key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+        const unsigned int base = tile * SORT_TILE + warp * (32 * SORT_ITEMS);
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; ++j) {
+            unsigned int e = base + j * 32 + lane;
+            bool ok = e < n;
+            key[j] = ok ? kin[e] : 0xffffffffu;
+            val[j] = ok ? vin[e] : 0u;
+            unsigned int d = (key[j] >> shift) & 255u;
+            unsigned int m = ok ? d : (256u + lane);
+            unsigned int peers = __match_any_sync(0xffffffffu, m);
+            unsigned int before = __popc(peers & ((1u << lane) - 1u));
+            unsigned int pre = ok ? s_wc[warp][d] : 0u;
+            __syncwarp();
+            if (ok && before == 0u) s_wc[warp][d] = pre + __popc(peers);
+            __syncwarp();
+            rank[j] = pre + before;
+        }
+        __syncthreads();
+        // thread d owns digit d: turn the per-warp counts into exclusive warp bases, get the tile total
+        unsigned int d = threadIdx.x, run = 0u;
+#pragma unroll
+        for (int wv = 0; wv < BP_BLOCK / 32; ++wv) {
+            unsigned int c = s_wc[wv][d];
+            s_wc[wv][d] = run;
+            run += c;
+        }
+        // chained scan over tiles, one chain per digit
+        unsigned int excl = 0u;
+        unsigned int *st = dstatus + (size_t) tile * 256u + d;
+        if (tile > 0) {
+            *reinterpret_cast<volatile unsigned int *>(st) = DS_AGG | run;
+            int t = (int) tile - 1;
+            for (;;) {
+                unsigned int sv;
+                const volatile unsigned int *ps = dstatus + (size_t) t * 256u + d;
+                do { sv = *ps; } while ((sv >> 30) == 0u);
+                excl += (sv & DS_VAL);
+                if ((sv >> 30) == 2u) break;
+                --t;
+            }
+        }
+        *reinterpret_cast<volatile unsigned int *>(st) = DS_PFX | (excl + run);
+        s_gb[d] = bin_base + excl;
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < SORT_ITEMS; ++j) {
+            unsigned int e = base + j * 32 + lane;
+            if (e < n) {
+                unsigned int dd = (key[j] >> shift) & 255u;
+                unsigned int pos = s_gb[dd] + s_wc[warp][dd] + rank[j];
+                kout[pos] = key[j];
+                vout[pos] = val[j];
+            }
+        }
+    }
+}
+
+static void launch_sort(const SortJob &job, long long cap, int max_passes, int max_blocks, cudaStream_t s) {
+    long long gh = (cap + BP_BLOCK * 8 - 1) / (BP_BLOCK * 8), gp = (cap + SORT_TILE - 1) / SORT_TILE;
+    int gridh = (int) (gh < 1 ? 1 : (gh > max_blocks ? max_blocks : gh));
+    int gridp = (int) (gp < 1 ? 1 : (gp > max_blocks ? max_blocks : gp));
+    k_sort_hist<<<gridh, BP_BLOCK, 0, s>>>(job);
+    for (int p = 0; p < max_passes; ++p) k_sort_pass<<<gridp, BP_BLOCK, 0, s>>>(job, p);
+}
+
+// ---- lexicographic (i, j) ordering of the candidate list: serial / parity mode only -------------
+__global__ void k_lex_init(DevWorld w, unsigned int *keys, unsigned int *vals) {
+    const unsigned int n = w.ctr->n_cand;
+    for (unsigned int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) {
+        keys[c] = (unsigned int) w.cand[c].y;
+        vals[c] = c;
+    }
+}
+__global__ void k_lex_mid(DevWorld w, const unsigned int *perm, unsigned int *keys) {
+    const unsigned int n = w.ctr->n_cand;
+    for (unsigned int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x)
+        keys[c] = (unsigned int) w.cand[perm[c]].x;
+}
+__global__ void k_lex_gather(DevWorld w, const unsigned int *perm, int2 *tmp) {
+    const unsigned int n = w.ctr->n_cand;
+    for (unsigned int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) tmp[c] = w.cand[perm[c]];
+}
+__global__ void k_lex_copy(DevWorld w, const int2 *tmp) {
+    const unsigned int n = w.ctr->n_cand;
+    for (unsigned int c = blockIdx.x * blockDim.x + threadIdx.x; c < n; c += gridDim.x * blockDim.x) w.cand[c] = tmp[c];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pair emission
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool pair_ok(unsigned int a, unsigned int b) {
+    unsigned int u = a | b;   // canonical cell: min-x column of one AND min-y row of one; some mass
+    return (u & ENT_MASS) && (u & ENT_X0) && (u & ENT_Y0);
+}
+
+__global__ void __launch_bounds__(BP_BLOCK) k_emit_pairs(DevWorld w, unsigned long long *status, unsigned int *ticket) {
+    const unsigned int n = w.ctr->n_entries;
+    const unsigned int sel = w.ctr->sort_passes & 1u;
+    const unsigned int *keys = w.keys[sel], *vals = w.vals[sel];
+    const unsigned int ntiles = (n + BP_BLOCK - 1) / BP_BLOCK;
+    if (ntiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.ctr->n_cand = 0;
+    for (;;) {
+        unsigned int tile = claim_tile(ticket);
+        if (tile >= ntiles) return;
+        unsigned int e = tile * BP_BLOCK + threadIdx.x;
+        unsigned int cnt = 0u, k = 0u, v = 0u;
+        if (e < n) {
+            k = keys[e];
+            v = vals[e];
+            for (unsigned int f = e + 1; f < n && keys[f] == k; ++f) cnt += pair_ok(v, vals[f]) ? 1u : 0u;
+        }
+        unsigned int total;
+        unsigned int excl = block_exclusive_scan<BP_BLOCK>(cnt, &total);
+        unsigned int base = tile_exclusive_prefix(status, tile, total);
+        if (cnt) {
+            unsigned int pos = base + excl;
+            for (unsigned int f = e + 1; f < n && keys[f] == k; ++f) {
+                unsigned int vf = vals[f];
+                if (pair_ok(v, vf)) {
+                    // entries of one cell are in ascending body order (stable sort of an ascending
+                    // emission), so ENT_BODY(v) < ENT_BODY(vf): the reference's i < j (world.c:333)
+                    if (pos < w.cap_cand) w.cand[pos] = make_int2((int) ENT_BODY(v), (int) ENT_BODY(vf));
+                    ++pos;
+                }
+            }
+        }
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            unsigned int c = base + total;
+            if (c > w.cap_cand) { atomicOr(&w.ctr->overflow, 2u); c = w.cap_cand; }
+            w.ctr->n_cand = c;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch surface
+// ---------------------------------------------------------------------------------------------
+static inline int grid_for(long long n, int block, int max_blocks) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int) g;
+}
+
+void fx_launch_integrate_velocity(const DevWorld &w, const FxLaunchCtx &cx) {
+    if (w.n == 0) return;
+    k_integrate_velocity<<<grid_for(w.n, BP_BLOCK, cx.max_blocks), BP_BLOCK, 0, cx.stream>>>(w);
+}
+
+void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_velocity) {
+    cudaStream_t s = cx.stream;
+    const int G = cx.max_blocks;
+    k_body_prepass<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, fuse_velocity ? 1 : 0, cx.status[0], cx.tickets + 0);
+    k_plan<<<1, 1, 0, s>>>(w);
+    k_emit_entries<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w);
+    k_emit_large<<<64, BP_BLOCK, 0, s>>>(w);
+    SortJob job;
+    job.keys[0] = w.keys[0]; job.keys[1] = w.keys[1]; job.vals[0] = w.vals[0]; job.vals[1] = w.vals[1];
+    job.n = &w.ctr->n_entries; job.passes_dev = &w.ctr->sort_passes; job.passes = 4;
+    job.ghist = cx.sort_hist; job.dstatus = cx.digit_status; job.dstatus_stride = cx.digit_status_stride;
+    job.tickets = cx.tickets + 8;
+    launch_sort(job, (long long) w.cap_entries, 4, G, s);
+    k_emit_pairs<<<grid_for((long long) w.cap_entries, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);
+}
+
+// Serial mode: reorder the candidate list into the reference's visiting order (i ascending, then j
+// ascending; src/broad_phase.c:167-178 + src/world.c:438-443).  Two stable LSD sorts of a
+// permutation (by j, then by i).  lex.* are scratch arrays of cap_cand elements.
+void fx_launch_lexsort_candidates(const DevWorld &w, const FxLaunchCtx &cx, const FxLexScratch &lex, int body_bits) {
+    cudaStream_t s = cx.stream;
+    const int G = cx.max_blocks, passes = (body_bits + 7) / 8;
+    const int g = grid_for((long long) w.cap_cand, BP_BLOCK, G);
+    for (int round = 0; round < 2; ++round) {
+        if (round == 0) k_lex_init<<<g, BP_BLOCK, 0, s>>>(w, lex.keys[0], lex.vals[0]);
+        SortJob job;
+        // after `passes` passes the data sits in buffer (passes & 1); round 1 starts from there
+        int src = (round == 0) ? 0 : (passes & 1);
+        if (round == 1) k_lex_mid<<<g, BP_BLOCK, 0, s>>>(w, lex.vals[src], lex.keys[src]);
+        job.keys[0] = lex.keys[src]; job.keys[1] = lex.keys[src ^ 1];
+        job.vals[0] = lex.vals[src]; job.vals[1] = lex.vals[src ^ 1];
+        job.n = &w.ctr->n_cand; job.passes_dev = nullptr; job.passes = (unsigned int) passes;
+        job.ghist = lex.ghist + round * 1024; job.dstatus = lex.dstatus + (size_t) round * 4 * lex.dstatus_stride;
+        job.dstatus_stride = lex.dstatus_stride; job.tickets = lex.tickets + round * 4;
+        launch_sort(job, (long long) w.cap_cand, passes, G, s);
+    }
+    const int fin = 0;   // round 0 ends in buffer (passes & 1), round 1 starts there and ends in buffer 0
+    k_lex_gather<<<g, BP_BLOCK, 0, s>>>(w, lex.vals[fin], lex.tmp);
+    k_lex_copy<<<g, BP_BLOCK, 0, s>>>(w, lex.tmp);
+}

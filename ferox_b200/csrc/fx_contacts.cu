@@ -1,0 +1,305 @@
+// fx_contacts.cu -- narrow phase over the candidate list + the GPU contact cache (kernels K5, K6).
+//
+// Replaces the body of the reference's pre-step callback, src/world.c:328-410: SAT per candidate
+// pair, contact-cache delete on a miss, warm-start transfer by contact id on a hit, material mixing
+// for new entries -- and the stale-entry eviction of src/world.c:222-235.
+//
+// Cache design.  The reference keeps one persistent stb_ds map (key = body pair) whose dense entry
+// array is what the solver iterates.  Here the dense array is REBUILT every step in a deterministic
+// order -- first this step's hits in candidate order, then the entries of the previous step that no
+// candidate touched (such stale entries keep being solved, they are not dropped)
+// -- and an open-addressing hash map (key = uidA<<32|uidB -> index into the previous dense array)
+// serves the warm-start lookups.  An entry of the previous array dies iff (a) a candidate with its
+// key missed (world.c:347-356), or (b) the timestamp rule fires (world.c:229-233), or (c) one of its
+// bodies left the world.
+//
+// HBM bytes (algorithmic): narrow phase C*(8 + 2*16 + 2*8 + shape bytes) read, 112 B per hit written,
+// one 12-byte hash probe per candidate; carry-over 112 B read+written per stale entry; hash rebuild
+// 12 B per slot cleared + 12 B per entry.
+#include "fx_device.h"
+#include "fx_kernels.h"
+#include "fx_narrow.cuh"
+#include "fx_scan.cuh"
+
+#define NP_BLOCK 256
+#define HASH_EMPTY 0xffffffffffffffffull
+
+__device__ __forceinline__ unsigned int hash_slot(unsigned long long key, unsigned int mask) {
+    unsigned long long z = (key ^ (key >> 31)) * 0x9E3779B97F4A7C15ull;
+    return (unsigned int) (z >> 32) & mask;
+}
+
+__device__ __forceinline__ int hash_find(const DevWorld &w, unsigned long long key) {
+    const unsigned int mask = w.cap_hash - 1u;
+    unsigned int s = hash_slot(key, mask);
+    for (unsigned int probes = 0; probes < w.cap_hash; ++probes) {
+        unsigned long long k = w.h_key[s];
+        if (k == key) return (int) w.h_val[s];
+        if (k == HASH_EMPTY) return -1;
+        s = (s + 1u) & mask;
+    }
+    return -1;
+}
+
+__device__ __forceinline__ Xf load_xf(const DevWorld &w, int i) {
+    float4 p = w.posrot[i];
+    Xf t;
+    t.p = v2(p.x, p.y);
+    t.sn = p.z;
+    t.cs = p.w;
+    return t;
+}
+
+__device__ __forceinline__ Xf shfl_xf(Xf t, int src) {
+    Xf r;
+    r.p.x = __shfl_sync(0xffffffffu, t.p.x, src);
+    r.p.y = __shfl_sync(0xffffffffu, t.p.y, src);
+    r.sn = __shfl_sync(0xffffffffu, t.sn, src);
+    r.cs = __shfl_sync(0xffffffffu, t.cs, src);
+    return r;
+}
+
+// One warp evaluates the 32 candidates its lanes hold: circle/circle per lane, everything else one
+// pair at a time with the whole warp (ballot work loop).  Returns the lane's own manifold.
+__device__ __forceinline__ void warp_narrowphase(const DevWorld &w, bool valid, int bi, int bj, Manifold &m) {
+    m.count = 0;
+    m.has_ids = 0;
+    int2 si = make_int2(-1, 0), sj = make_int2(-1, 0);
+    Xf ti = { { 0.f, 0.f }, 0.f, 1.f }, tj = ti;
+    if (valid) {
+        si = w.shape[bi];
+        sj = w.shape[bj];
+        ti = load_xf(w, bi);
+        tj = load_xf(w, bj);
+    }
+    const bool has_shapes = valid && si.x >= 0 && sj.x >= 0;
+    const bool cc = has_shapes && si.y == FX_SHAPE_CIRCLE && sj.y == FX_SHAPE_CIRCLE;
+    if (cc) collide_circles(w.shapes[si.x].radius, ti, w.shapes[sj.x].radius, tj, m);
+    unsigned int todo = __ballot_sync(0xffffffffu, has_shapes && !cc);
+    while (todo) {
+        int src = __ffs(todo) - 1;
+        todo &= todo - 1u;
+        int a = __shfl_sync(0xffffffffu, si.x, src), b = __shfl_sync(0xffffffffu, sj.x, src);
+        Xf ta = shfl_xf(ti, src), tb = shfl_xf(tj, src);
+        Manifold mm;
+        warp_collide(&w.shapes[a], ta, &w.shapes[b], tb, mm);
+        if ((int) lane_id() == src) m = mm;
+    }
+}
+
+__global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned long long *status, unsigned int *ticket) {
+    const unsigned int ncand = w.ctr->n_cand;
+    const unsigned int ntiles = (ncand + NP_BLOCK - 1) / NP_BLOCK;
+    const int cs = *w.cur_flip;
+    const ManifoldSet cur = w.man[cs], prev = w.man[cs ^ 1];
+    if (ntiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.ctr->n_hits = 0;
+    for (;;) {
+        unsigned int tile = claim_tile(ticket);
+        if (tile >= ntiles) return;
+        const unsigned int c = tile * NP_BLOCK + threadIdx.x;
+        const bool valid = c < ncand;
+        int2 pr = valid ? w.cand[c] : make_int2(0, 0);
+        Manifold m;
+        warp_narrowphase(w, valid, pr.x, pr.y, m);
+        const bool hit = valid && m.count > 0;
+
+        // contact-cache probe (hit or miss): src/world.c:347-394
+        unsigned long long key = 0ull;
+        int old = -1;
+        float friction = 0.0f, restitution = 0.0f;
+        float lam_n[2] = { 0.0f, 0.0f }, lam_t[2] = { 0.0f, 0.0f };
+        if (valid) {
+            key = ((unsigned long long) w.uid[pr.x] << 32) | (unsigned long long) w.uid[pr.y];
+            old = hash_find(w, key);
+            if (old >= 0) w.touched[old] = 1;
+            w.cand_hit[c] = hit ? 1 : 0;
+        }
+        if (hit) {
+            if (old >= 0) {
+                float4 oh = prev.hdr[old];
+                friction = oh.z;
+                restitution = oh.w;
+                int ocount = prev.meta[old].x;
+                int oid0 = prev.cid[2 * old], oid1 = prev.cid[2 * old + 1];
+                for (int i = 0; i < m.count; ++i) {
+                    int oi = -1;
+                    if (ocount > 0 && m.id[i] == oid0) oi = 0;
+                    else if (ocount > 1 && m.id[i] == oid1) oi = 1;
+                    if (oi < 0) continue;
+                    float4 oimp = prev.imp[2 * old + oi];
+                    lam_n[i] = oimp.y;
+                    lam_t[i] = oimp.w;
+                }
+            } else {                                   // new entry: src/world.c:395-404
+                const ShapeDev *s1 = &w.shapes[w.shape[pr.x].x], *s2 = &w.shapes[w.shape[pr.y].x];
+                friction = 0.5f * (s1->friction + s2->friction);
+                restitution = pin_fminf(s1->restitution, s2->restitution);
+                if (friction < 0.0f) friction = 0.0f;
+                if (restitution < 0.0f) restitution = 0.0f;
+            }
+        }
+        unsigned int total;
+        unsigned int excl = block_exclusive_scan<NP_BLOCK>(hit ? 1u : 0u, &total);
+        unsigned int base = tile_exclusive_prefix(status, tile, total);
+        if (hit) {
+            unsigned int pos = base + excl;
+            if (pos < w.cap_manifolds) {
+                cur.key[pos] = make_uint2(w.uid[pr.x], w.uid[pr.y]);
+                cur.body[pos] = pr;
+                cur.hdr[pos] = make_float4(m.dir.x, m.dir.y, friction, restitution);
+                cur.meta[pos] = make_int2(m.count, -1);
+                // contacts[1] of a one-point manifold is a copy taken BEFORE stamping / warm-start
+                // transfer (src/collision.c:292,374,...; src/world.c:362-394): id/point/depth only
+                cur.geo[2 * pos] = make_float4(m.p[0].x, m.p[0].y, m.depth[0], w.timestamp);
+                cur.geo[2 * pos + 1] = make_float4(m.p[1].x, m.p[1].y, m.depth[1], (m.count > 1) ? w.timestamp : 0.0f);
+                cur.imp[2 * pos] = make_float4(0.0f, lam_n[0], 0.0f, lam_t[0]);
+                cur.imp[2 * pos + 1] = make_float4(0.0f, (m.count > 1) ? lam_n[1] : 0.0f, 0.0f, (m.count > 1) ? lam_t[1] : 0.0f);
+                cur.cid[2 * pos] = m.id[0];
+                cur.cid[2 * pos + 1] = m.id[1];
+            }
+        }
+        // contact points of this tile -> Q
+        unsigned int q = hit ? (unsigned int) m.count : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+        if (lane_id() == 0 && q) atomicAdd(&w.ctr->n_contacts, q);
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            unsigned int h = base + total;
+            if (h > w.cap_manifolds) { atomicOr(&w.ctr->overflow, 4u); h = w.cap_manifolds; }
+            w.ctr->n_hits = h;
+        }
+    }
+}
+
+// stale entries of the previous array that no candidate probed survive (App. A.7) unless the
+// timestamp rule (src/world.c:229-233) or a departed body removes them
+__global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned long long *status, unsigned int *ticket) {
+    const unsigned int nprev = *w.prev_count;
+    const unsigned int ntiles = (nprev + NP_BLOCK - 1) / NP_BLOCK;
+    const int cs = *w.cur_flip;
+    const ManifoldSet cur = w.man[cs], prev = w.man[cs ^ 1];
+    const unsigned int nhits = w.ctr->n_hits;
+    if (ntiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.ctr->n_manifolds = nhits;
+    for (;;) {
+        unsigned int tile = claim_tile(ticket);
+        if (tile >= ntiles) return;
+        const unsigned int p = tile * NP_BLOCK + threadIdx.x;
+        bool keep = false;
+        int2 body = make_int2(-1, -1);
+        int count = 0;
+        if (p < nprev && !w.touched[p]) {
+            uint2 k = prev.key[p];
+            body.x = w.idx_of_uid[k.x];
+            body.y = w.idx_of_uid[k.y];
+            count = prev.meta[p].x;
+            keep = body.x >= 0 && body.y >= 0;
+            for (int c = 0; c < count && keep; ++c)
+                if (w.timestamp - prev.geo[2 * p + c].w > w.dt) keep = false;
+        }
+        unsigned int total;
+        unsigned int excl = block_exclusive_scan<NP_BLOCK>(keep ? 1u : 0u, &total);
+        unsigned int base = tile_exclusive_prefix(status, tile, total);
+        if (keep) {
+            unsigned int pos = nhits + base + excl;
+            if (pos < w.cap_manifolds) {
+                cur.key[pos] = prev.key[p];
+                cur.body[pos] = body;
+                cur.hdr[pos] = prev.hdr[p];
+                cur.meta[pos] = make_int2(count, -1);
+                cur.geo[2 * pos] = prev.geo[2 * p];
+                cur.geo[2 * pos + 1] = prev.geo[2 * p + 1];
+                cur.imp[2 * pos] = prev.imp[2 * p];
+                cur.imp[2 * pos + 1] = prev.imp[2 * p + 1];
+                cur.cid[2 * pos] = prev.cid[2 * p];
+                cur.cid[2 * pos + 1] = prev.cid[2 * p + 1];
+            }
+        }
+        unsigned int q = keep ? (unsigned int) count : 0u;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
+        if (lane_id() == 0 && q) atomicAdd(&w.ctr->n_contacts, q);
+        if (tile == ntiles - 1 && threadIdx.x == 0) {
+            unsigned int mcount = nhits + base + total;
+            if (mcount > w.cap_manifolds) { atomicOr(&w.ctr->overflow, 4u); mcount = w.cap_manifolds; }
+            w.ctr->n_manifolds = mcount;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NP_BLOCK) k_hash_build(DevWorld w) {
+    const unsigned int m = w.ctr->n_manifolds;
+    const ManifoldSet cur = w.man[*w.cur_flip];
+    const unsigned int mask = w.cap_hash - 1u;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        uint2 k = cur.key[i];
+        unsigned long long key = ((unsigned long long) k.x << 32) | (unsigned long long) k.y;
+        unsigned int s = hash_slot(key, mask);
+        for (;;) {
+            unsigned long long prevk = atomicCAS(&w.h_key[s], HASH_EMPTY, key);
+            if (prevk == HASH_EMPTY || prevk == key) { w.h_val[s] = i; break; }
+            s = (s + 1u) & mask;
+        }
+    }
+}
+
+// after the table was re-allocated: index the PREVIOUS dense array again (warm-start lookups)
+__global__ void __launch_bounds__(NP_BLOCK) k_hash_build_prev(DevWorld w) {
+    const unsigned int m = *w.prev_count;
+    const ManifoldSet prev = w.man[*w.cur_flip ^ 1];
+    const unsigned int mask = w.cap_hash - 1u;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
+        uint2 k = prev.key[i];
+        unsigned long long key = ((unsigned long long) k.x << 32) | (unsigned long long) k.y;
+        unsigned int s = hash_slot(key, mask);
+        for (;;) {
+            unsigned long long prevk = atomicCAS(&w.h_key[s], HASH_EMPTY, key);
+            if (prevk == HASH_EMPTY || prevk == key) { w.h_val[s] = i; break; }
+            s = (s + 1u) & mask;
+        }
+    }
+}
+
+static inline int grid_for(long long n, int block, int max_blocks) {
+    long long g = (n + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > max_blocks) g = max_blocks;
+    return (int) g;
+}
+
+void fx_launch_rehash_prev(const DevWorld &w, const FxLaunchCtx &cx) {
+    k_hash_build_prev<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, cx.stream>>>(w);
+}
+
+void fx_launch_narrowphase(const DevWorld &w, const FxLaunchCtx &cx) {
+    cudaStream_t s = cx.stream;
+    cudaMemsetAsync(w.touched, 0, w.cap_manifolds, s);
+    k_narrowphase<<<grid_for((long long) w.cap_cand, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[2], cx.tickets + 6);
+}
+
+void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx) {
+    cudaStream_t s = cx.stream;
+    k_carry_over<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7);
+    cudaMemsetAsync(w.h_key, 0xff, (size_t) w.cap_hash * sizeof(unsigned long long), s);
+    k_hash_build<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w);
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched stand-alone narrow phase (frComputeCollision / frxComputeCollisions)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(NP_BLOCK) k_collide_pairs(DevWorld w, const int2 *pairs, int n, Manifold *out) {
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (n + stride - 1) / stride;
+    for (int r = 0; r < rounds; ++r) {
+        int c = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        bool valid = c < n;
+        int2 pr = valid ? pairs[c] : make_int2(0, 0);
+        Manifold m;
+        warp_narrowphase(w, valid, pr.x, pr.y, m);
+        if (valid) out[c] = m;
+    }
+}
+
+void fx_launch_collide_pairs(const DevWorld &w, const FxLaunchCtx &cx, const int2 *pairs, int n, Manifold *out) {
+    if (n <= 0) return;
+    k_collide_pairs<<<grid_for(n, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, cx.stream>>>(w, pairs, n, out);
+}

@@ -1,0 +1,141 @@
+// fx_host.h -- host-side objects behind the opaque ferox.h handles.
+//
+// frShape / frBody / frWorld / frSpatialHash are opaque in the public API (reference
+// include/ferox.h:138-155), so their layout is ours.  A body keeps its slowly-changing properties
+// itself; its DYNAMIC state (transform, velocity, force accumulator, AABB) lives in the packed rows
+// below -- inside the body while it is outside a world, inside the world's pinned host mirror of the
+// device struct-of-arrays while it is in one.  The device copy is authoritative after a step;
+// getters pull it back lazily (one bulk D2H per step at most), setters mark rows dirty for the next
+// bulk H2D.
+#pragma once
+#include <cstdint>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/ferox_b200.h"
+#include "fx_device.h"
+#include "fx_kernels.h"
+
+struct frShape_ {
+    frShapeType type;
+    frMaterial material;
+    float area;
+    float radius;
+    frVertices vertices, normals;
+};
+
+// packed dynamic state of one body; the same packing as the device arrays (fx_device.h)
+struct BodyRow {
+    float4 posrot;   // x, y, sin, cos
+    float angle;
+    float4 vel;      // vx, vy, omega, invMass
+    float4 mprop;    // mass, invInertia, gravityScale, bits(type | flags << 8)
+    float4 force;    // fx, fy, torque, 0
+    float4 aabb;     // x, y, w, h
+};
+
+struct frBody_ {
+    frBodyType type;
+    frBodyFlags flags;
+    frShape *shape;
+    float mass, inv_mass, inertia, inv_inertia, gravity_scale;
+    void *ctx;
+    frWorld *world;      // non-null while the body is a member of world->bodies
+    int index;           // world index while in a world
+    uint32_t uid;        // stable id while in a world (contact-cache key)
+    BodyRow loc;         // dynamic state while outside a world
+};
+
+enum { FX_OP_ADD = 1, FX_OP_REMOVE = 2 };   // reference src/world.c:35-39
+struct WorldOp {
+    int id;
+    frBody *body;
+};
+
+// dirty bits of the host mirror (which arrays must be uploaded before the next step)
+enum {
+    FX_DIRTY_POSROT = 1, FX_DIRTY_ANGLE = 2, FX_DIRTY_VEL = 4, FX_DIRTY_MPROP = 8, FX_DIRTY_FORCE = 16,
+    FX_DIRTY_AABB = 32, FX_DIRTY_SHAPE = 64, FX_DIRTY_UID = 128, FX_DIRTY_ALL = 255
+};
+
+struct HostMirror {     // pinned host arrays, capacity `cap`
+    int cap = 0;
+    float4 *posrot = nullptr, *vel = nullptr, *mprop = nullptr, *force = nullptr, *aabb = nullptr;
+    float *angle = nullptr;
+    int2 *shape = nullptr;
+    unsigned int *uid = nullptr;
+};
+
+struct frWorld_ {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    frVector2 gravity{ 0.f, 0.f };
+    float cell = 0.f;
+    std::vector<frBody *> bodies;
+    // deferred add/remove queue: ring of pow2(capacity) slots, one unusable
+    // (reference src/external/ferox_utils.h:172-219, src/world.c:113-115)
+    std::vector<WorldOp> ring;
+    int ring_head = 0, ring_tail = 0;
+    int capacity = FR_WORLD_MAX_OBJECT_COUNT;
+    float accumulator = 0.f, timestamp = 0.f;
+    frCollisionHandler handler{ nullptr, nullptr };
+    int solver_mode = FRX_SOLVER_COLORED;
+
+    HostMirror h;
+    unsigned dirty = 0;
+    bool device_newer = false;       // device state advanced past the host mirror
+    bool needs_sizing = true;        // run the sizing pre-pass before the next step
+    bool device_ok = false;
+
+    // shape table
+    std::vector<frShape *> shape_list;
+    std::unordered_map<const frShape *, int> shape_index;
+    std::vector<ShapeDev> shape_host;
+    ShapeDev *d_shapes = nullptr;
+    int d_shapes_cap = 0;
+    uint64_t shape_epoch_seen = 0;
+
+    // uid allocator
+    std::vector<int> uid_index;          // uid -> world index or -1
+    std::vector<uint32_t> uid_free, uid_pending_free;
+    int *d_idx_of_uid = nullptr;
+    int d_uid_cap = 0;
+    bool uid_dirty = true;
+
+    DevWorld dw{};
+    FxLaunchCtx cx{};
+    int body_cap = 0;
+    // serial-mode extras
+    FxLexScratch lex{};
+    SerialOrder so{};
+    unsigned int so_cap = 0, lex_cap = 0;
+
+    StepCountersDev *d_snapshot = nullptr;
+    StepCountersDev *h_snapshot = nullptr;      // pinned
+    cudaEvent_t snapshot_ready = nullptr;
+    bool snapshot_pending = false;
+    StepCountersDev last{};                     // last snapshot read back
+    long long steps = 0;
+    long long sticky_overflow = 0;
+    long long manifold_hint = 0;
+};
+
+struct frSpatialHash_;
+
+// ---- internal helpers shared between the host translation units ----
+uint64_t fx_shape_epoch();
+void fx_shape_touch();
+frAABB fx_shape_aabb(const frShape *s, frTransform tx);
+void fx_body_recompute_mass(frBody *b);
+BodyRow *fx_row(frBody *b);                 // current dynamic row for writing (pulls + marks dirty)
+const BodyRow fx_row_read(const frBody *b); // current dynamic row (pulls if the device is newer)
+void fx_world_pull(frWorld *w);
+void fx_world_mark(frWorld *w, unsigned bits);
+void fx_set_error(int code, const char *what);
+bool fx_cuda_ok(cudaError_t e, const char *what);
+
+// kernels' extra launchers (fx_bodies.cu)
+void fx_launch_finish_step(const DevWorld &w, const FxLaunchCtx &cx, StepCountersDev *snapshot);
+void fx_launch_single_body(const DevWorld &w, cudaStream_t s, int i, int op, float dt);
+void fx_launch_single_pair_solve(const DevWorld &w, cudaStream_t s, CollisionPod *col, int op, float inv_dt);
+void fx_launch_sincos(const float *a, int n, float *s, float *c, cudaStream_t st);

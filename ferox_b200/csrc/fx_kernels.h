@@ -1,0 +1,70 @@
+// fx_kernels.h -- host-callable launch surface of the step kernels (implemented in the .cu files).
+#pragma once
+#include "fx_device.h"
+
+// Per-world launch scratch: stream, grid cap, and the zero-initialised words the ordered (look-back)
+// sweeps need.  `fx_launch_begin_step` clears them; each sweep owns one status region + one ticket.
+struct FxLaunchCtx {
+    cudaStream_t stream;
+    int max_blocks;                 // grid cap for grid-stride kernels (multiple of the SM count)
+    int coop_blocks;                // co-resident grid of the cooperative solver kernel
+    unsigned long long *status[4];  // 0 body prepass, 1 pair emission, 2 narrow phase, 3 carry-over
+    size_t status_words[4];
+    unsigned int *tickets;          // [16]
+    unsigned int *sort_hist;        // [4][256]
+    unsigned int *digit_status;     // [4][digit_status_stride]
+    size_t digit_status_stride;
+    void *zero_base;                // one allocation backs everything above; cleared per step
+    size_t zero_bytes;
+};
+
+// one LSD radix sort of (key, value) u32 pairs: ping-pong buffers, element count on the device
+struct SortJob {
+    unsigned int *keys[2], *vals[2];
+    const unsigned int *n;
+    const unsigned int *passes_dev;   // device-side pass count (nullptr: use `passes`)
+    unsigned int passes;
+    unsigned int *ghist;              // [4][256], zeroed
+    unsigned int *dstatus;            // [4][dstatus_stride], zeroed
+    size_t dstatus_stride;
+    unsigned int *tickets;            // [4], zeroed
+};
+
+// scratch of the serial-mode candidate ordering (allocated only when that mode is used)
+struct FxLexScratch {
+    unsigned int *keys[2], *vals[2];
+    int2 *tmp;
+    unsigned int *ghist;     // [2][4][256]
+    unsigned int *dstatus;   // [2][4][dstatus_stride]
+    size_t dstatus_stride;
+    unsigned int *tickets;   // [8]
+    void *zero_base;
+    size_t zero_bytes;
+};
+
+// reference-order bookkeeping of the serial solver (fx_solve.cu)
+struct SerialOrder {
+    unsigned long long *r_key;   // keys in reference array order
+    unsigned int *r_len;
+    unsigned long long *t_key;   // open-addressing index key -> position in r_key
+    unsigned int *t_val;
+    unsigned int t_cap;
+};
+
+void fx_launch_begin_step(const DevWorld &w, const FxLaunchCtx &cx);
+void fx_launch_integrate_velocity(const DevWorld &w, const FxLaunchCtx &cx);
+void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_velocity);
+void fx_launch_lexsort_candidates(const DevWorld &w, const FxLaunchCtx &cx, const FxLexScratch &lex, int body_bits);
+void fx_launch_narrowphase(const DevWorld &w, const FxLaunchCtx &cx);
+void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx);
+void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint);
+void fx_launch_serial_order(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o);
+void fx_launch_solve_serial_with(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, int iterations);
+void fx_launch_integrate_position(const DevWorld &w, const FxLaunchCtx &cx);
+void fx_launch_finish_step(const DevWorld &w, const FxLaunchCtx &cx);
+int fx_query_coop_blocks(int device);
+void fx_launch_rehash_prev(const DevWorld &w, const FxLaunchCtx &cx);
+void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o);
+
+// single-pair / utility entry points (used by the public per-body functions and the tests)
+void fx_launch_collide_pairs(const DevWorld &w, const FxLaunchCtx &cx, const int2 *pairs, int n, Manifold *out);

@@ -1,0 +1,419 @@
+// fx_solve.cu -- contact colouring, warm start and the Projected Gauss-Seidel sweeps (K7-K9).
+//
+// Replaces reference src/world.c:237-249 (warm start over the cache array, then
+// FR_WORLD_ITERATION_COUNT sweeps of frResolveCollision in array order).
+//
+// COLOURED MODE (production).  The whole solve is ONE cooperative kernel; phases are separated by
+// grid-wide barriers instead of kernel launches (10 iterations x ~7 colours + warm start is ~80
+// dependent phases; a launch per phase would cost more than the phases themselves):
+//   1. greedy colouring of the manifold graph (two manifolds conflict iff they share a body that
+//      the solver WRITES: invMass > 0 or invInertia > 0; static/kinematic bodies are read-only,
+//      SURVEY.md App. A.13): Luby-style rounds, a manifold takes the lowest colour free on both
+//      bodies when it holds the minimum (hashed) ticket on both; tickets go through atomicMin, so
+//      the colouring is deterministic.
+//   2. counting sort of manifold indices by colour -> `order`.
+//   3. per colour: build the colour-major solver records (lever arms, unit perpendiculars, bias,
+//      effective masses -- everything that depends on positions only) and apply the warm start.
+//   4. iterations x colours: one thread per manifold streams its record, gathers the two body
+//      velocities {vx, vy, omega, invMass} (16 B each), updates both contacts, scatters.
+//   5. accumulated impulses + effective masses are written back to the cache.
+// Per Gauss-Seidel sweep the algorithmic traffic is 44 B + 2*32 B per manifold and 56 B + 8 B per
+// contact (SURVEY.md section 8d counts 80 M + 36 Q; we keep r1/r2/u1/u2 precomputed: +24 B/contact).
+//
+// SERIAL MODE (parity).  One thread visits the manifolds in the reference's cache-array order
+// (maintained by k_serial_order, which replays the stb_ds insertion / swap-delete discipline,
+// reference src/external/stb_ds.h:1436-1448, 1506-1520) with the same per-contact arithmetic
+// (fx_solver.cuh), which makes a step bit-comparable with the CPU reference.
+#include <cooperative_groups.h>
+
+#include "fx_device.h"
+#include "fx_kernels.h"
+#include "fx_scan.cuh"
+#include "fx_solver.cuh"
+
+namespace cg = cooperative_groups;
+
+#define SV_BLOCK 256
+
+__device__ __forceinline__ unsigned int ticket_of(unsigned int m, unsigned int round) {
+    // bijection on 26 bits (odd multipliers and xor-shifts are invertible), so tickets are unique
+    unsigned int x = m & 0x3ffffffu;
+    x = (x * 0x2545F49u) & 0x3ffffffu;
+    x ^= x >> 13;
+    x = (x * 0x1E3779Bu) & 0x3ffffffu;
+    x ^= x >> 11;
+    return ((63u - round) << 26) | x;
+}
+
+__device__ __forceinline__ bool body_is_written(const DevWorld &w, int i) {
+    return w.vel[i].w > 0.0f || w.mprop[i].y > 0.0f;
+}
+
+struct BodyS {
+    float4 v;   // vx, vy, omega, invMass
+};
+
+// build the solver record of manifold m at slot s and apply its warm start (src/rigid_body.c:333-411)
+__device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const ManifoldSet &man, unsigned int m,
+                                                       unsigned int s) {
+    const int2 b = man.body[m];
+    const float4 hdr = man.hdr[m];
+    const int count = man.meta[m].x;
+    const V2 n = v2(hdr.x, hdr.y);
+    const V2 t = vperp_right(n);
+    float4 va4 = w.vel[b.x], vb4 = w.vel[b.y];
+    const float inv_ma = va4.w, inv_mb = vb4.w;
+    const float inv_ia = w.mprop[b.x].y, inv_ib = w.mprop[b.y].y;
+    const float4 pa4 = w.posrot[b.x], pb4 = w.posrot[b.y];
+    w.sol.body[s] = b;
+    w.sol.nt[s] = make_float4(n.x, n.y, t.x, t.y);
+    w.sol.mat[s] = make_float4(hdr.z, hdr.w, inv_ia, inv_ib);
+    const bool active = (inv_ma + inv_mb > 0.0f);           // src/rigid_body.c:338
+    w.sol.count_src[s] = (active ? count : 0) | (int) (m << 2);
+    if (!active) {
+        // static bodies are brought to rest (src/rigid_body.c:339-347); nothing else happens
+        const int ta = __float_as_int(w.mprop[b.x].w) & 0xff, tb = __float_as_int(w.mprop[b.y].w) & 0xff;
+        if (ta == FX_BODY_STATIC) w.vel[b.x] = make_float4(0.f, 0.f, 0.f, va4.w);
+        if (tb == FX_BODY_STATIC) w.vel[b.y] = make_float4(0.f, 0.f, 0.f, vb4.w);
+        return;
+    }
+    Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
+    for (int c = 0; c < count; ++c) {
+        const float4 g = man.geo[2 * m + c];
+        const float4 im = man.imp[2 * m + c];
+        ContactK k;
+        contact_arms(k, v2(g.x, g.y), v2(pa4.x, pa4.y), v2(pb4.x, pb4.y));
+        k.bias = contact_bias(g.z, w.inv_dt);
+        contact_masses(k, n, t, inv_ma, inv_mb, inv_ia, inv_ib);
+        contact_warm_start(k, n, t, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
+        w.sol.r[2 * s + c] = make_float4(k.r1.x, k.r1.y, k.r2.x, k.r2.y);
+        w.sol.u[2 * s + c] = make_float4(k.u1.x, k.u1.y, k.u2.x, k.u2.y);
+        w.sol.k[2 * s + c] = make_float4(k.bias, k.nmass, k.tmass, 0.0f);
+        w.sol.lam[2 * s + c] = make_float2(im.y, im.w);
+    }
+    w.vel[b.x] = make_float4(va.x, va.y, va.w, inv_ma);
+    w.vel[b.y] = make_float4(vb.x, vb.y, vb.w, inv_mb);
+}
+
+__device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s) {
+    const int cs = w.sol.count_src[s];
+    const int count = cs & 3;
+    if (count == 0) return;
+    const int2 b = w.sol.body[s];
+    const float4 nt = w.sol.nt[s];
+    const float4 mat = w.sol.mat[s];
+    float4 va4 = w.vel[b.x], vb4 = w.vel[b.y];
+    Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
+    const V2 n = v2(nt.x, nt.y), t = v2(nt.z, nt.w);
+    for (int c = 0; c < count; ++c) {
+        const float4 r = w.sol.r[2 * s + c], u = w.sol.u[2 * s + c], kk = w.sol.k[2 * s + c];
+        float2 lam = w.sol.lam[2 * s + c];
+        ContactK k;
+        k.r1 = v2(r.x, r.y); k.r2 = v2(r.z, r.w);
+        k.u1 = v2(u.x, u.y); k.u2 = v2(u.z, u.w);
+        k.bias = kk.x; k.nmass = kk.y; k.tmass = kk.z;
+        contact_resolve(k, n, t, mat.x, mat.y, lam.x, lam.y, va4.w, vb4.w, mat.z, mat.w, va, vb);
+        w.sol.lam[2 * s + c] = lam;
+    }
+    w.vel[b.x] = make_float4(va.x, va.y, va.w, va4.w);
+    w.vel[b.y] = make_float4(vb.x, vb.y, vb.w, vb4.w);
+}
+
+__global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iterations) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned int s_hist[FX_MAX_COLORS];
+    __shared__ unsigned int s_off[FX_MAX_COLORS + 1];
+    __shared__ unsigned int s_ncolors;
+    const ManifoldSet man = w.man[*w.cur_flip];
+    const unsigned int M = w.ctr->n_manifolds;
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    unsigned int *color_cnt = w.color_scratch, *color_fill = w.color_scratch + FX_MAX_COLORS,
+                 *color_rem = w.color_scratch + 2 * FX_MAX_COLORS;
+
+    // ---- phase 0: reset per-body colouring state, find the bodies that constrain each manifold
+    for (unsigned int i = tid; i < (unsigned int) w.n; i += nth) {
+        w.body_mask[i] = 0ull;
+        w.winner[i] = 0xffffffffu;
+    }
+    for (unsigned int m = tid; m < M; m += nth) {
+        int2 b = man.body[m];
+        w.cbody[m] = make_int2(body_is_written(w, b.x) ? b.x : -1, body_is_written(w, b.y) ? b.y : -1);
+    }
+    for (unsigned int i = tid; i < 3 * FX_MAX_COLORS; i += nth) w.color_scratch[i] = 0u;
+    grid.sync();
+
+    // ---- phase 1: colouring rounds
+    for (unsigned int round = 0; round < 64u; ++round) {
+        for (unsigned int m = tid; m < M; m += nth) {
+            if (man.meta[m].y >= 0) continue;
+            int2 cb = w.cbody[m];
+            unsigned int tk = ticket_of(m, round);
+            if (cb.x >= 0) atomicMin(&w.winner[cb.x], tk);
+            if (cb.y >= 0) atomicMin(&w.winner[cb.y], tk);
+        }
+        grid.sync();
+        unsigned int left = 0u;
+        for (unsigned int m = tid; m < M; m += nth) {
+            int2 meta = man.meta[m];
+            if (meta.y >= 0) continue;
+            int2 cb = w.cbody[m];
+            unsigned int tk = ticket_of(m, round);
+            bool won = (cb.x < 0 || w.winner[cb.x] == tk) && (cb.y < 0 || w.winner[cb.y] == tk);
+            if (!won) { ++left; continue; }
+            unsigned long long used = (cb.x >= 0 ? w.body_mask[cb.x] : 0ull) | (cb.y >= 0 ? w.body_mask[cb.y] : 0ull);
+            int col = __ffsll((long long) ~used) - 1;
+            if (col < 0) { col = FX_MAX_COLORS - 1; atomicOr(&w.ctr->overflow, 8u); }
+            meta.y = col;
+            man.meta[m] = meta;
+            if (cb.x >= 0) w.body_mask[cb.x] |= (1ull << col);
+            if (cb.y >= 0) w.body_mask[cb.y] |= (1ull << col);
+        }
+        if (left) atomicAdd(&color_rem[round], left);
+        grid.sync();
+        if (color_rem[round] == 0u) break;
+    }
+
+    // ---- phase 2: counting sort of manifold indices by colour
+    if (threadIdx.x < FX_MAX_COLORS) s_hist[threadIdx.x] = 0u;
+    __syncthreads();
+    for (unsigned int m = tid; m < M; m += nth) {
+        int col = man.meta[m].y;
+        if (col < 0) { col = FX_MAX_COLORS - 1; atomicOr(&w.ctr->overflow, 8u); }   // > 64 rounds
+        atomicAdd(&s_hist[col], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < FX_MAX_COLORS && s_hist[threadIdx.x]) atomicAdd(&color_cnt[threadIdx.x], s_hist[threadIdx.x]);
+    grid.sync();
+    if (threadIdx.x == 0) {
+        unsigned int run = 0u, nc = 0u;
+        for (int c = 0; c < FX_MAX_COLORS; ++c) {
+            s_off[c] = run;
+            unsigned int k = color_cnt[c];
+            run += k;
+            if (k) nc = (unsigned int) c + 1u;
+        }
+        s_off[FX_MAX_COLORS] = run;
+        s_ncolors = nc;
+        if (blockIdx.x == 0) {
+            for (int c = 0; c <= FX_MAX_COLORS; ++c) w.color_off[c] = s_off[c];
+            w.ctr->n_colors = nc;
+        }
+    }
+    __syncthreads();
+    for (unsigned int base = blockIdx.x * blockDim.x; base < M; base += nth) {
+        unsigned int m = base + threadIdx.x;
+        int col = -1;
+        if (m < M) { col = man.meta[m].y; if (col < 0) col = FX_MAX_COLORS - 1; }
+        // warp-aggregated cursor bump: one atomic per distinct colour per warp
+        unsigned int peers = __match_any_sync(0xffffffffu, col);
+        unsigned int before = __popc(peers & ((1u << lane_id()) - 1u));
+        unsigned int pos = 0u;
+        if (col >= 0 && before == 0u) pos = atomicAdd(&color_fill[col], (unsigned int) __popc(peers));
+        pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1);
+        if (col >= 0) w.order[s_off[col] + pos + before] = m;
+    }
+    grid.sync();
+
+    // ---- phase 3: solver records + warm start, one colour at a time
+    const unsigned int ncolors = s_ncolors;
+    for (unsigned int c = 0; c < ncolors; ++c) {
+        for (unsigned int s = s_off[c] + tid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s);
+        grid.sync();
+    }
+    // ---- phase 4: Gauss-Seidel sweeps
+    for (int it = 0; it < iterations; ++it)
+        for (unsigned int c = 0; c < ncolors; ++c) {
+            for (unsigned int s = s_off[c] + tid; s < s_off[c + 1]; s += nth) sweep_one(w, s);
+            grid.sync();
+        }
+    // ---- phase 5: write the impulses and effective masses back to the cache
+    for (unsigned int s = tid; s < M; s += nth) {
+        const int cs = w.sol.count_src[s];
+        const unsigned int m = (unsigned int) cs >> 2;
+        const int count = cs & 3;
+        for (int c = 0; c < count; ++c) {
+            float4 kk = w.sol.k[2 * s + c];
+            float2 lam = w.sol.lam[2 * s + c];
+            man.imp[2 * m + c] = make_float4(kk.y, lam.x, kk.z, lam.y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// serial (reference-order) mode
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int so_slot(unsigned long long key, unsigned int mask) {
+    unsigned long long z = (key ^ (key >> 29)) * 0xBF58476D1CE4E5B9ull;
+    return (unsigned int) (z >> 32) & mask;
+}
+__device__ int so_find(const SerialOrder &o, unsigned long long key) {
+    unsigned int mask = o.t_cap - 1u, s = so_slot(key, mask);
+    for (;;) {
+        unsigned long long k = o.t_key[s];
+        if (k == key) return (int) s;
+        if (k == 0xffffffffffffffffull) return -1;
+        s = (s + 1u) & mask;
+    }
+}
+__device__ void so_put(const SerialOrder &o, unsigned long long key) {   // hmputs: in place or append
+    if (so_find(o, key) >= 0) return;
+    unsigned int pos = (*o.r_len)++;
+    o.r_key[pos] = key;
+    unsigned int mask = o.t_cap - 1u, s = so_slot(key, mask);
+    while (o.t_key[s] != 0xffffffffffffffffull) s = (s + 1u) & mask;
+    o.t_key[s] = key;
+    o.t_val[s] = pos;
+}
+__device__ void so_del(const SerialOrder &o, unsigned long long key) {   // hmdel: swap-delete
+    int s = so_find(o, key);
+    if (s < 0) return;
+    unsigned int old_index = o.t_val[s], final_index = *o.r_len - 1u;
+    unsigned int mask = o.t_cap - 1u, hole = (unsigned int) s, j = (unsigned int) s;
+    for (;;) {   // backward-shift deletion
+        j = (j + 1u) & mask;
+        unsigned long long kj = o.t_key[j];
+        if (kj == 0xffffffffffffffffull) break;
+        unsigned int home = so_slot(kj, mask);
+        if (((j - home) & mask) >= ((j - hole) & mask)) {
+            o.t_key[hole] = kj;
+            o.t_val[hole] = o.t_val[j];
+            hole = j;
+        }
+    }
+    o.t_key[hole] = 0xffffffffffffffffull;
+    if (old_index != final_index) {
+        unsigned long long moved = o.r_key[final_index];
+        o.r_key[old_index] = moved;
+        o.t_val[so_find(o, moved)] = old_index;
+    }
+    *o.r_len = final_index;
+}
+
+__device__ __forceinline__ int cache_lookup(const DevWorld &w, unsigned long long key) {
+    const unsigned int mask = w.cap_hash - 1u;
+    unsigned long long z = (key ^ (key >> 31)) * 0x9E3779B97F4A7C15ull;
+    unsigned int s = (unsigned int) (z >> 32) & mask;
+    for (;;) {
+        unsigned long long k = w.h_key[s];
+        if (k == key) return (int) w.h_val[s];
+        if (k == 0xffffffffffffffffull) return -1;
+        s = (s + 1u) & mask;
+    }
+}
+
+// replay this step's candidate outcomes (lexicographic order) on the reference-order key array,
+// then the eviction loop of src/world.c:222-235 and the removal of entries that did not survive
+__global__ void k_serial_order(DevWorld w, SerialOrder o) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const unsigned int ncand = w.ctr->n_cand;
+    for (unsigned int c = 0; c < ncand; ++c) {
+        int2 pr = w.cand[c];
+        unsigned long long key = ((unsigned long long) w.uid[pr.x] << 32) | (unsigned long long) w.uid[pr.y];
+        if (w.cand_hit[c]) so_put(o, key);
+        else so_del(o, key);
+    }
+    // entries that the new dense array no longer holds (timestamp rule, departed bodies): the
+    // reference walks j = 0 .. entryCount-1 of the pre-loop length while hmdel shrinks the array, so
+    // the element swapped into slot j is skipped (App. A.7); replayed here on the key array
+    unsigned int entry_count = *o.r_len;
+    for (unsigned int j = 0; j < entry_count; ++j) {
+        if (j >= *o.r_len) break;   // (the reference reads stale tail bytes here; not replayed)
+        unsigned long long key = o.r_key[j];
+        if (cache_lookup(w, key) < 0) so_del(o, key);
+    }
+    // anything still missing (skipped by the quirk above but gone from the dense array) must go,
+    // otherwise the solver would dereference a missing entry
+    for (unsigned int j = 0; j < *o.r_len;) {
+        if (cache_lookup(w, o.r_key[j]) < 0) so_del(o, o.r_key[j]);
+        else ++j;
+    }
+}
+
+__global__ void k_serial_reindex(SerialOrder o) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const unsigned int len = *o.r_len, mask = o.t_cap - 1u;
+    for (unsigned int p = 0; p < len; ++p) {
+        unsigned long long key = o.r_key[p];
+        unsigned int s = so_slot(key, mask);
+        while (o.t_key[s] != 0xffffffffffffffffull) s = (s + 1u) & mask;
+        o.t_key[s] = key;
+        o.t_val[s] = p;
+    }
+}
+
+__global__ void k_solve_serial(DevWorld w, SerialOrder o, int iterations) {
+    if (blockIdx.x != 0 || threadIdx.x != 0) return;
+    const ManifoldSet man = w.man[*w.cur_flip];
+    const unsigned int len = *o.r_len;
+    for (int it = -1; it < iterations; ++it) {
+        for (unsigned int r = 0; r < len; ++r) {
+            int m = cache_lookup(w, o.r_key[r]);
+            if (m < 0) continue;
+            const int2 b = man.body[m];
+            const float4 hdr = man.hdr[m];
+            const int count = man.meta[m].x;
+            const V2 n = v2(hdr.x, hdr.y), t = vperp_right(n);
+            float4 va4 = w.vel[b.x], vb4 = w.vel[b.y];
+            const float inv_ma = va4.w, inv_mb = vb4.w, inv_ia = w.mprop[b.x].y, inv_ib = w.mprop[b.y].y;
+            if (!(inv_ma + inv_mb > 0.0f)) {
+                if (it < 0) {
+                    const int ta = __float_as_int(w.mprop[b.x].w) & 0xff, tb = __float_as_int(w.mprop[b.y].w) & 0xff;
+                    if (ta == FX_BODY_STATIC) w.vel[b.x] = make_float4(0.f, 0.f, 0.f, va4.w);
+                    if (tb == FX_BODY_STATIC) w.vel[b.y] = make_float4(0.f, 0.f, 0.f, vb4.w);
+                }
+                continue;
+            }
+            const float4 pa4 = w.posrot[b.x], pb4 = w.posrot[b.y];
+            Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
+            for (int c = 0; c < count; ++c) {
+                const float4 g = man.geo[2 * m + c];
+                float4 im = man.imp[2 * m + c];
+                ContactK k;
+                contact_arms(k, v2(g.x, g.y), v2(pa4.x, pa4.y), v2(pb4.x, pb4.y));
+                if (it < 0) {
+                    contact_masses(k, n, t, inv_ma, inv_mb, inv_ia, inv_ib);
+                    im.x = k.nmass;
+                    im.z = k.tmass;
+                    contact_warm_start(k, n, t, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
+                } else {
+                    k.bias = contact_bias(g.z, w.inv_dt);
+                    k.nmass = im.x;
+                    k.tmass = im.z;
+                    contact_resolve(k, n, t, hdr.z, hdr.w, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
+                }
+                man.imp[2 * m + c] = im;
+            }
+            w.vel[b.x] = make_float4(va.x, va.y, va.w, inv_ma);
+            w.vel[b.y] = make_float4(vb.x, vb.y, vb.w, inv_mb);
+        }
+    }
+    w.ctr->n_colors = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch surface
+// ---------------------------------------------------------------------------------------------
+int fx_query_coop_blocks(int device) {
+    int sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_colored, SV_BLOCK, 0);
+    if (per_sm > 4) per_sm = 4;
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;
+}
+
+void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint) {
+    long long want = (work_hint + SV_BLOCK - 1) / SV_BLOCK;
+    int blocks = (int) (want < 1 ? 1 : (want > cx.coop_blocks ? cx.coop_blocks : want));
+    DevWorld wc = w;
+    void *args[] = { (void *) &wc, (void *) &iterations };
+    cudaLaunchCooperativeKernel((const void *) k_solve_colored, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);
+}
+
+void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o) { k_serial_reindex<<<1, 32, 0, cx.stream>>>(o); }
+void fx_launch_serial_order(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o) {
+    k_serial_order<<<1, 32, 0, cx.stream>>>(w, o);
+}
+void fx_launch_solve_serial_with(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, int iterations) {
+    k_solve_serial<<<1, 32, 0, cx.stream>>>(w, o, iterations);
+}

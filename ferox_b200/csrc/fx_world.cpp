@@ -1,0 +1,1201 @@
+// fx_world.cpp -- the world container, host<->device state management and the step driver.
+//
+// Replaces reference src/world.c: frCreateWorld ... frUpdateWorld (:107-285), the deferred add/remove
+// queue (:147-167, :450-479) and the collision-handler sweeps (:209-214, :254-259).  frStepWorld
+// launches the kernel sequence of fx_broadphase.cu / fx_contacts.cu / fx_solve.cu / fx_bodies.cu on
+// the world's stream; nothing of the step runs on the host, and a world without a usable CUDA
+// device refuses to step (sticky error + stderr), it never falls back to the CPU.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "fx_host.h"
+
+// ---------------------------------------------------------------------------------------------
+// errors, device selection
+// ---------------------------------------------------------------------------------------------
+static int g_error = 0;
+static char g_error_text[256] = "no error";
+static thread_local int g_device = -1;
+
+void fx_set_error(int code, const char *what) {
+    if (g_error == 0) {
+        g_error = code;
+        std::snprintf(g_error_text, sizeof g_error_text, "%s", what);
+    }
+    std::fprintf(stderr, "[ferox-b200] ERROR %d: %s\n", code, what);
+}
+bool fx_cuda_ok(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return true;
+    char buf[256];
+    std::snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    fx_set_error(1000 + (int) e, buf);
+    return false;
+}
+extern "C" int frxGetLastError(void) { return g_error; }
+extern "C" const char *frxGetLastErrorString(void) { return g_error_text; }
+extern "C" int frxSetDevice(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return -1;
+    g_device = device;
+    return 0;
+}
+static int current_device() {
+    if (g_device >= 0) return g_device;
+    const char *e = std::getenv("FEROX_DEVICE");
+    return e ? std::atoi(e) : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// small allocation helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+static bool dev_realloc(T *&p, size_t old_count, size_t new_count, cudaStream_t s, bool keep) {
+    T *q = nullptr;
+    if (!fx_cuda_ok(cudaMalloc((void **) &q, (new_count ? new_count : 1) * sizeof(T)), "cudaMalloc")) return false;
+    if (keep && p && old_count)
+        fx_cuda_ok(cudaMemcpyAsync(q, p, (old_count < new_count ? old_count : new_count) * sizeof(T), cudaMemcpyDeviceToDevice, s), "grow copy");
+    if (p) { cudaStreamSynchronize(s); cudaFree(p); }
+    p = q;
+    return true;
+}
+template <typename T>
+static bool pin_realloc(T *&p, size_t old_count, size_t new_count) {
+    T *q = nullptr;
+    if (!fx_cuda_ok(cudaMallocHost((void **) &q, (new_count ? new_count : 1) * sizeof(T)), "cudaMallocHost")) return false;
+    std::memset(q, 0, (new_count ? new_count : 1) * sizeof(T));
+    if (p && old_count) std::memcpy(q, p, (old_count < new_count ? old_count : new_count) * sizeof(T));
+    if (p) cudaFreeHost(p);
+    p = q;
+    return true;
+}
+static unsigned int pow2_at_least(unsigned long long v) {
+    unsigned long long p = 1;
+    while (p < v) p <<= 1;
+    return (unsigned int) (p > 0x80000000ull ? 0x80000000ull : p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// world life cycle
+// ---------------------------------------------------------------------------------------------
+static int default_capacity() {
+    const char *e = std::getenv("FEROX_MAX_OBJECT_COUNT");
+    int v = e ? std::atoi(e) : 0;
+    return v > 0 ? v : FR_WORLD_MAX_OBJECT_COUNT;
+}
+static void ring_resize(frWorld *w, int capacity) {
+    unsigned int len = pow2_at_least((unsigned long long) (capacity > 1 ? capacity : 1));
+    w->ring.assign(len, WorldOp{ 0, nullptr });
+    w->ring_head = w->ring_tail = 0;
+}
+
+static bool world_device_init(frWorld *w) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        fx_set_error(1, "no CUDA device: the ferox world step has no CPU fallback");
+        return false;
+    }
+    w->device = current_device();
+    if (w->device >= n) w->device = 0;
+    if (!fx_cuda_ok(cudaSetDevice(w->device), "cudaSetDevice")) return false;
+    if (!fx_cuda_ok(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return false;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
+    w->cx.stream = w->stream;
+    w->cx.max_blocks = sms * 8;
+    w->cx.coop_blocks = fx_query_coop_blocks(w->device);
+    fx_cuda_ok(cudaMalloc((void **) &w->d_snapshot, sizeof(StepCountersDev)), "cudaMalloc");
+    fx_cuda_ok(cudaMallocHost((void **) &w->h_snapshot, sizeof(StepCountersDev)), "cudaMallocHost");
+    std::memset(w->h_snapshot, 0, sizeof(StepCountersDev));
+    fx_cuda_ok(cudaEventCreateWithFlags(&w->snapshot_ready, cudaEventDisableTiming), "cudaEventCreate");
+    fx_cuda_ok(cudaMalloc((void **) &w->dw.ctr, sizeof(StepCountersDev)), "cudaMalloc");
+    fx_cuda_ok(cudaMalloc((void **) &w->dw.prev_count, sizeof(unsigned int)), "cudaMalloc");
+    fx_cuda_ok(cudaMalloc((void **) &w->dw.cur_flip, sizeof(int)), "cudaMalloc");
+    fx_cuda_ok(cudaMalloc((void **) &w->dw.color_off, (FX_MAX_COLORS + 1) * sizeof(unsigned int)), "cudaMalloc");
+    fx_cuda_ok(cudaMalloc((void **) &w->dw.color_scratch, 3 * FX_MAX_COLORS * sizeof(unsigned int)), "cudaMalloc");
+    cudaMemsetAsync(w->dw.ctr, 0, sizeof(StepCountersDev), w->stream);
+    cudaMemsetAsync(w->dw.prev_count, 0, sizeof(unsigned int), w->stream);
+    cudaMemsetAsync(w->dw.cur_flip, 0, sizeof(int), w->stream);
+    w->device_ok = (g_error == 0) || true;
+    return fx_cuda_ok(cudaStreamSynchronize(w->stream), "world init");
+}
+
+extern "C" frWorld *frCreateWorld(frVector2 gravity, float cellSize) {
+    frWorld *w = new (std::nothrow) frWorld_();
+    if (!w) return nullptr;
+    w->gravity = gravity;
+    w->cell = cellSize;
+    w->capacity = default_capacity();
+    ring_resize(w, w->capacity);
+    const char *mode = std::getenv("FEROX_SOLVER");
+    if (mode && std::strcmp(mode, "serial") == 0) w->solver_mode = FRX_SOLVER_SERIAL;
+    w->device_ok = world_device_init(w);
+    return w;
+}
+
+static void free_manifold_set(ManifoldSet &m) {
+    cudaFree(m.key); cudaFree(m.body); cudaFree(m.hdr); cudaFree(m.meta); cudaFree(m.geo); cudaFree(m.imp); cudaFree(m.cid);
+    std::memset(&m, 0, sizeof m);
+}
+static void world_free_device(frWorld *w) {
+    if (w->stream) cudaStreamSynchronize(w->stream);
+    DevWorld &d = w->dw;
+    cudaFree(d.posrot); cudaFree(d.vel); cudaFree(d.mprop); cudaFree(d.force); cudaFree(d.aabb); cudaFree(d.angle);
+    cudaFree(d.shape); cudaFree(d.uid); cudaFree(w->d_idx_of_uid); cudaFree(w->d_shapes);
+    cudaFree(d.cell_cnt); cudaFree(d.cell_off); cudaFree(d.large_list);
+    cudaFree(d.keys[0]); cudaFree(d.keys[1]); cudaFree(d.vals[0]); cudaFree(d.vals[1]);
+    cudaFree(d.cand); cudaFree(d.cand_hit);
+    free_manifold_set(d.man[0]); free_manifold_set(d.man[1]);
+    cudaFree(d.touched); cudaFree(d.h_key); cudaFree(d.h_val);
+    cudaFree(d.sol.body); cudaFree(d.sol.nt); cudaFree(d.sol.mat); cudaFree(d.sol.count_src);
+    cudaFree(d.sol.r); cudaFree(d.sol.u); cudaFree(d.sol.k); cudaFree(d.sol.lam);
+    cudaFree(d.order); cudaFree(d.color_off); cudaFree(d.body_mask); cudaFree(d.winner); cudaFree(d.cbody);
+    cudaFree(d.color_scratch); cudaFree(d.ctr); cudaFree(d.prev_count); cudaFree(d.cur_flip);
+    cudaFree(w->cx.zero_base);
+    cudaFree(w->lex.keys[0]); cudaFree(w->lex.keys[1]); cudaFree(w->lex.vals[0]); cudaFree(w->lex.vals[1]);
+    cudaFree(w->lex.tmp); cudaFree(w->lex.zero_base);
+    cudaFree(w->so.r_key); cudaFree(w->so.r_len); cudaFree(w->so.t_key); cudaFree(w->so.t_val);
+    cudaFree(w->d_snapshot);
+    if (w->h_snapshot) cudaFreeHost(w->h_snapshot);
+    HostMirror &h = w->h;
+    if (h.posrot) cudaFreeHost(h.posrot);
+    if (h.vel) cudaFreeHost(h.vel);
+    if (h.mprop) cudaFreeHost(h.mprop);
+    if (h.force) cudaFreeHost(h.force);
+    if (h.aabb) cudaFreeHost(h.aabb);
+    if (h.angle) cudaFreeHost(h.angle);
+    if (h.shape) cudaFreeHost(h.shape);
+    if (h.uid) cudaFreeHost(h.uid);
+    if (w->snapshot_ready) cudaEventDestroy(w->snapshot_ready);
+    if (w->stream) cudaStreamDestroy(w->stream);
+}
+
+static void detach_body(frWorld *w, frBody *b);
+
+extern "C" void frReleaseWorld(frWorld *w) {
+    if (!w) return;
+    if (w->device_ok) { cudaSetDevice(w->device); fx_world_pull(w); }
+    // frees every body that is currently a member (src/world.c:124-125), not the queued ones
+    for (frBody *b : w->bodies) std::free(b);
+    w->bodies.clear();
+    if (w->device_ok || w->stream) world_free_device(w);
+    delete w;
+}
+
+extern "C" void frClearWorld(frWorld *w) {
+    if (!w) return;
+    fx_world_pull(w);
+    // src/world.c:138-144: the bodies are neither freed nor is the contact cache cleared
+    while (!w->bodies.empty()) detach_body(w, w->bodies.back());
+    w->needs_sizing = true;
+}
+
+static bool ring_push(frWorld *w, WorldOp op) {
+    const int mask = (int) w->ring.size() - 1;
+    if (((w->ring_head + 1) & mask) == w->ring_tail) return false;
+    w->ring[w->ring_head] = op;
+    w->ring_head = (w->ring_head + 1) & mask;
+    return true;
+}
+extern "C" bool frAddBodyToWorld(frWorld *w, frBody *b) {
+    if (!w || !b || (int) w->bodies.size() >= w->capacity) return false;
+    return ring_push(w, WorldOp{ FX_OP_ADD, b });
+}
+extern "C" bool frRemoveBodyFromWorld(frWorld *w, frBody *b) {
+    if (!w || !b) return false;
+    return ring_push(w, WorldOp{ FX_OP_REMOVE, b });
+}
+extern "C" bool frIsBodyInWorld(const frWorld *w, frBody *b) {
+    if (!w || !b) return false;
+    return b->world == w && b->index >= 0 && b->index < (int) w->bodies.size() && w->bodies[b->index] == b;
+}
+extern "C" frBody *frGetBodyInWorld(const frWorld *w, int i) {
+    if (!w || i < 0 || i >= (int) w->bodies.size()) return nullptr;
+    return w->bodies[i];
+}
+extern "C" int frGetBodyCountInWorld(const frWorld *w) { return w ? (int) w->bodies.size() : 0; }
+extern "C" frVector2 frGetWorldGravity(const frWorld *w) {
+    frVector2 z = { 0.f, 0.f };
+    return w ? w->gravity : z;
+}
+extern "C" void frSetWorldCollisionHandler(frWorld *w, frCollisionHandler handler) { if (w) w->handler = handler; }
+extern "C" void frSetWorldGravity(frWorld *w, frVector2 gravity) { if (w) w->gravity = gravity; }
+
+extern "C" bool frxSetWorldCapacity(frWorld *w, int maxObjectCount) {
+    if (!w || maxObjectCount <= 0 || w->ring_head != w->ring_tail) return false;
+    w->capacity = maxObjectCount;
+    ring_resize(w, maxObjectCount);
+    return true;
+}
+extern "C" int frxGetWorldCapacity(const frWorld *w) { return w ? w->capacity : 0; }
+extern "C" void frxSetWorldSolverMode(frWorld *w, int mode) {
+    if (w && (mode == FRX_SOLVER_COLORED || mode == FRX_SOLVER_SERIAL)) w->solver_mode = mode;
+}
+extern "C" int frxGetWorldSolverMode(const frWorld *w) { return w ? w->solver_mode : 0; }
+extern "C" void frxSetWorldTimestamp(frWorld *w, float t) { if (w) w->timestamp = t; }
+extern "C" float frxGetWorldTimestamp(const frWorld *w) { return w ? w->timestamp : 0.0f; }
+
+// ---------------------------------------------------------------------------------------------
+// host mirror <-> device
+// ---------------------------------------------------------------------------------------------
+static bool ensure_body_capacity(frWorld *w, int need) {
+    if (need <= w->body_cap) return true;
+    int cap = w->body_cap ? w->body_cap : 1024;
+    while (cap < need) cap *= 2;
+    const size_t o = (size_t) w->body_cap, n = (size_t) cap;
+    HostMirror &h = w->h;
+    bool ok = pin_realloc(h.posrot, o, n) && pin_realloc(h.vel, o, n) && pin_realloc(h.mprop, o, n) &&
+              pin_realloc(h.force, o, n) && pin_realloc(h.aabb, o, n) && pin_realloc(h.angle, o, n) &&
+              pin_realloc(h.shape, o, n) && pin_realloc(h.uid, o, n);
+    h.cap = cap;
+    DevWorld &d = w->dw;
+    cudaStream_t s = w->stream;
+    ok = ok && dev_realloc(d.posrot, o, n, s, true) && dev_realloc(d.vel, o, n, s, true) && dev_realloc(d.mprop, o, n, s, true) &&
+         dev_realloc(d.force, o, n, s, true) && dev_realloc(d.aabb, o, n, s, true) && dev_realloc(d.angle, o, n, s, true) &&
+         dev_realloc(d.shape, o, n, s, true) && dev_realloc(d.uid, o, n, s, true) &&
+         dev_realloc(d.cell_cnt, 0, n, s, false) && dev_realloc(d.cell_off, 0, n, s, false) &&
+         dev_realloc(d.large_list, 0, n, s, false) && dev_realloc(d.body_mask, 0, n, s, false) &&
+         dev_realloc(d.winner, 0, n, s, false);
+    d.cap_large = (unsigned int) n;
+    w->body_cap = cap;
+    return ok;
+}
+
+void fx_world_mark(frWorld *w, unsigned bits) {
+    w->dirty |= bits;
+    if (bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) w->needs_sizing = true;
+}
+
+// bring the pinned host mirror up to date with the device (one bulk D2H per dynamic array)
+void fx_world_pull(frWorld *w) {
+    if (!w || !w->device_newer) return;
+    w->device_newer = false;
+    const size_t n = w->bodies.size();
+    if (n == 0 || !w->device_ok) return;
+    cudaSetDevice(w->device);
+    cudaStream_t s = w->stream;
+    cudaMemcpyAsync(w->h.posrot, w->dw.posrot, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(w->h.angle, w->dw.angle, n * sizeof(float), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(w->h.vel, w->dw.vel, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(w->h.aabb, w->dw.aabb, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    fx_cuda_ok(cudaStreamSynchronize(s), "state download");
+    std::memset(w->h.force, 0, n * sizeof(float4));   // cleared by the step (src/world.c:481-482)
+}
+
+static void world_push(frWorld *w) {
+    const size_t n = w->bodies.size();
+    cudaStream_t s = w->stream;
+    const unsigned d = w->dirty;
+    if (n && d) {
+        if (d & FX_DIRTY_POSROT) cudaMemcpyAsync(w->dw.posrot, w->h.posrot, n * sizeof(float4), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_ANGLE) cudaMemcpyAsync(w->dw.angle, w->h.angle, n * sizeof(float), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_VEL) cudaMemcpyAsync(w->dw.vel, w->h.vel, n * sizeof(float4), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_MPROP) cudaMemcpyAsync(w->dw.mprop, w->h.mprop, n * sizeof(float4), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_FORCE) cudaMemcpyAsync(w->dw.force, w->h.force, n * sizeof(float4), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_AABB) cudaMemcpyAsync(w->dw.aabb, w->h.aabb, n * sizeof(float4), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_SHAPE) cudaMemcpyAsync(w->dw.shape, w->h.shape, n * sizeof(int2), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_UID) cudaMemcpyAsync(w->dw.uid, w->h.uid, n * sizeof(unsigned int), cudaMemcpyHostToDevice, s);
+    }
+    w->dirty = 0;
+    if (w->uid_dirty) {
+        const size_t m = w->uid_index.size();
+        if ((int) m > w->d_uid_cap) {
+            int cap = w->d_uid_cap ? w->d_uid_cap : 1024;
+            while (cap < (int) m) cap *= 2;
+            dev_realloc(w->d_idx_of_uid, 0, (size_t) cap, s, false);
+            w->d_uid_cap = cap;
+        }
+        if (m) {
+            // pageable source: the copy is staged synchronously, which is what we want here
+            cudaMemcpyAsync(w->d_idx_of_uid, w->uid_index.data(), m * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaStreamSynchronize(s);
+        }
+        w->uid_dirty = false;
+    }
+}
+
+// ---- shape table ----
+static void fill_shape_dev(ShapeDev &d, const frShape *s) {
+    std::memset(&d, 0, sizeof d);
+    d.type = (int) s->type;
+    d.nv = (s->type == FR_SHAPE_POLYGON) ? s->vertices.count : 0;
+    d.radius = s->radius;
+    d.friction = s->material.friction;
+    d.restitution = s->material.restitution;
+    for (int k = 0; k < d.nv && k < FX_MAX_VERTS; ++k) {
+        d.verts[k] = v2(s->vertices.data[k].x, s->vertices.data[k].y);
+        d.normals[k] = v2(s->normals.data[k].x, s->normals.data[k].y);
+    }
+}
+static int shape_slot(frWorld *w, frShape *s) {
+    if (!s) return -1;
+    auto it = w->shape_index.find(s);
+    if (it != w->shape_index.end()) return it->second;
+    int idx = (int) w->shape_list.size();
+    w->shape_list.push_back(s);
+    w->shape_index.emplace(s, idx);
+    w->shape_host.emplace_back();
+    fill_shape_dev(w->shape_host.back(), s);
+    w->shape_epoch_seen = 0;   // force an upload
+    return idx;
+}
+static void refresh_body_shape_rows(frWorld *w) {
+    for (size_t i = 0; i < w->bodies.size(); ++i) {
+        frBody *b = w->bodies[i];
+        int slot = shape_slot(w, b->shape);
+        w->h.shape[i] = make_int2(slot, b->shape ? (int) b->shape->type : 0);
+    }
+    w->dirty |= FX_DIRTY_SHAPE;
+}
+static bool sync_shapes(frWorld *w) {
+    if (w->shape_epoch_seen == fx_shape_epoch() && !(w->dirty & FX_DIRTY_SHAPE)) return true;
+    // a shape was created/edited somewhere, or a body changed its shape: rebuild the rows
+    refresh_body_shape_rows(w);
+    for (size_t i = 0; i < w->shape_list.size(); ++i) fill_shape_dev(w->shape_host[i], w->shape_list[i]);
+    const int n = (int) w->shape_list.size();
+    if (n > w->d_shapes_cap) {
+        int cap = w->d_shapes_cap ? w->d_shapes_cap : 64;
+        while (cap < n) cap *= 2;
+        if (!dev_realloc(w->d_shapes, 0, (size_t) cap, w->stream, false)) return false;
+        w->d_shapes_cap = cap;
+    }
+    if (n) {
+        cudaMemcpyAsync(w->d_shapes, w->shape_host.data(), (size_t) n * sizeof(ShapeDev), cudaMemcpyHostToDevice, w->stream);
+        cudaStreamSynchronize(w->stream);
+    }
+    w->dw.shapes = w->d_shapes;
+    w->dw.n_shapes = n;
+    w->shape_epoch_seen = fx_shape_epoch();
+    return true;
+}
+
+// ---- membership ----
+static void attach_body(frWorld *w, frBody *b) {
+    fx_world_pull(w);
+    const int i = (int) w->bodies.size();
+    ensure_body_capacity(w, i + 1);
+    uint32_t uid;
+    if (!w->uid_free.empty()) { uid = w->uid_free.back(); w->uid_free.pop_back(); }
+    else { uid = (uint32_t) w->uid_index.size(); w->uid_index.push_back(-1); }
+    w->uid_index[uid] = i;
+    w->uid_dirty = true;
+    HostMirror &h = w->h;
+    h.posrot[i] = b->loc.posrot; h.angle[i] = b->loc.angle; h.vel[i] = b->loc.vel; h.mprop[i] = b->loc.mprop;
+    h.force[i] = b->loc.force; h.aabb[i] = b->loc.aabb;
+    h.shape[i] = make_int2(shape_slot(w, b->shape), b->shape ? (int) b->shape->type : 0);
+    h.uid[i] = uid;
+    b->world = w; b->index = i; b->uid = uid;
+    w->bodies.push_back(b);
+    w->dirty = FX_DIRTY_ALL;
+    w->needs_sizing = true;
+}
+static void detach_body(frWorld *w, frBody *b) {
+    fx_world_pull(w);
+    const int i = b->index, last = (int) w->bodies.size() - 1;
+    HostMirror &h = w->h;
+    b->loc.posrot = h.posrot[i]; b->loc.angle = h.angle[i]; b->loc.vel = h.vel[i]; b->loc.mprop = h.mprop[i];
+    b->loc.force = h.force[i]; b->loc.aabb = h.aabb[i];
+    w->uid_index[b->uid] = -1;
+    w->uid_pending_free.push_back(b->uid);
+    w->uid_dirty = true;
+    if (i != last) {   // swap-with-last renumbering, src/world.c:463-469
+        frBody *m = w->bodies[last];
+        h.posrot[i] = h.posrot[last]; h.angle[i] = h.angle[last]; h.vel[i] = h.vel[last]; h.mprop[i] = h.mprop[last];
+        h.force[i] = h.force[last]; h.aabb[i] = h.aabb[last]; h.shape[i] = h.shape[last]; h.uid[i] = h.uid[last];
+        w->bodies[i] = m;
+        m->index = i;
+        w->uid_index[m->uid] = i;
+    }
+    w->bodies.pop_back();
+    b->world = nullptr; b->index = -1;
+    w->dirty = FX_DIRTY_ALL;
+    w->needs_sizing = true;
+}
+
+// frPostStepWorld's queue drain, src/world.c:450-479
+static void drain_queue(frWorld *w) {
+    const int mask = (int) w->ring.size() - 1;
+    while (w->ring_head != w->ring_tail) {
+        WorldOp op = w->ring[w->ring_tail];
+        w->ring_tail = (w->ring_tail + 1) & mask;
+        if (op.id == FX_OP_ADD) {
+            if (op.body->world != nullptr) continue;   // duplicate adds / foreign bodies are not supported
+            attach_body(w, op.body);
+        } else if (op.id == FX_OP_REMOVE) {
+            if (op.body->world == w) detach_body(w, op.body);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// work buffers
+// ---------------------------------------------------------------------------------------------
+static bool alloc_manifold_set(ManifoldSet &m, size_t old_cap, size_t cap, cudaStream_t s, bool keep) {
+    return dev_realloc(m.key, old_cap, cap, s, keep) && dev_realloc(m.body, old_cap, cap, s, keep) &&
+           dev_realloc(m.hdr, old_cap, cap, s, keep) && dev_realloc(m.meta, old_cap, cap, s, keep) &&
+           dev_realloc(m.geo, 2 * old_cap, 2 * cap, s, keep) && dev_realloc(m.imp, 2 * old_cap, 2 * cap, s, keep) &&
+           dev_realloc(m.cid, 2 * old_cap, 2 * cap, s, keep);
+}
+
+static bool rebuild_zero_region(frWorld *w) {
+    // status words of the ordered sweeps + tickets + sort histograms + per-digit chain status
+    DevWorld &d = w->dw;
+    FxLaunchCtx &cx = w->cx;
+    size_t tiles_body = (size_t) w->body_cap / 256 + 2, tiles_ent = (size_t) d.cap_entries / 256 + 2;
+    size_t tiles_cand = (size_t) d.cap_cand / 256 + 2, tiles_man = (size_t) d.cap_manifolds / 256 + 2;
+    size_t sort_tiles = (size_t) d.cap_entries / 2048 + 2;
+    cx.status_words[0] = tiles_body; cx.status_words[1] = tiles_ent; cx.status_words[2] = tiles_cand; cx.status_words[3] = tiles_man;
+    cx.digit_status_stride = sort_tiles * 256;
+    size_t bytes = (tiles_body + tiles_ent + tiles_cand + tiles_man) * sizeof(unsigned long long) + 16 * sizeof(unsigned int) +
+                   4 * 256 * sizeof(unsigned int) + 4 * cx.digit_status_stride * sizeof(unsigned int);
+    if (cx.zero_base) { cudaStreamSynchronize(w->stream); cudaFree(cx.zero_base); cx.zero_base = nullptr; }
+    if (!fx_cuda_ok(cudaMalloc(&cx.zero_base, bytes), "cudaMalloc scratch")) return false;
+    cx.zero_bytes = bytes;
+    char *p = (char *) cx.zero_base;
+    for (int k = 0; k < 4; ++k) { cx.status[k] = (unsigned long long *) p; p += cx.status_words[k] * sizeof(unsigned long long); }
+    cx.tickets = (unsigned int *) p; p += 16 * sizeof(unsigned int);
+    cx.sort_hist = (unsigned int *) p; p += 4 * 256 * sizeof(unsigned int);
+    cx.digit_status = (unsigned int *) p;
+    return true;
+}
+
+static bool ensure_work_capacity(frWorld *w, unsigned long long ent, unsigned long long cand, unsigned long long man) {
+    DevWorld &d = w->dw;
+    cudaStream_t s = w->stream;
+    bool changed = false, ok = true;
+    if (ent > d.cap_entries) {
+        unsigned int cap = (unsigned int) (ent < 0x7fffffffull ? ent : 0x7fffffffull);
+        ok = ok && dev_realloc(d.keys[0], 0, cap, s, false) && dev_realloc(d.keys[1], 0, cap, s, false) &&
+             dev_realloc(d.vals[0], 0, cap, s, false) && dev_realloc(d.vals[1], 0, cap, s, false);
+        d.cap_entries = cap;
+        changed = true;
+    }
+    if (cand > d.cap_cand) {
+        unsigned int cap = (unsigned int) (cand < 0x7fffffffull ? cand : 0x7fffffffull);
+        ok = ok && dev_realloc(d.cand, 0, cap, s, false) && dev_realloc(d.cand_hit, 0, cap, s, false);
+        d.cap_cand = cap;
+        changed = true;
+    }
+    if (man > d.cap_manifolds) {
+        const size_t o = d.cap_manifolds;
+        unsigned int cap = (unsigned int) (man < 0x3ffffffull ? man : 0x3ffffffull);   // 26-bit colouring tickets
+        ok = ok && alloc_manifold_set(d.man[0], o, cap, s, true) && alloc_manifold_set(d.man[1], o, cap, s, true);
+        ok = ok && dev_realloc(d.touched, 0, cap, s, false) && dev_realloc(d.cbody, 0, cap, s, false) &&
+             dev_realloc(d.order, 0, cap, s, false);
+        ok = ok && dev_realloc(d.sol.body, 0, cap, s, false) && dev_realloc(d.sol.nt, 0, cap, s, false) &&
+             dev_realloc(d.sol.mat, 0, cap, s, false) && dev_realloc(d.sol.count_src, 0, cap, s, false) &&
+             dev_realloc(d.sol.r, 0, 2 * (size_t) cap, s, false) && dev_realloc(d.sol.u, 0, 2 * (size_t) cap, s, false) &&
+             dev_realloc(d.sol.k, 0, 2 * (size_t) cap, s, false) && dev_realloc(d.sol.lam, 0, 2 * (size_t) cap, s, false);
+        // the hash map indexes the PREVIOUS dense array: rebuild it at the new size from that array
+        unsigned int hcap = pow2_at_least(2ull * cap + 16);
+        const unsigned int old_h = d.cap_hash;
+        ok = ok && dev_realloc(d.h_key, 0, hcap, s, false) && dev_realloc(d.h_val, 0, hcap, s, false);
+        d.cap_hash = hcap;
+        d.cap_manifolds = cap;
+        cudaMemsetAsync(d.h_key, 0xff, (size_t) hcap * sizeof(unsigned long long), s);
+        if (old_h) fx_launch_rehash_prev(d, w->cx);
+        changed = true;
+    }
+    if (changed) ok = ok && rebuild_zero_region(w);
+    return ok;
+}
+
+static bool ensure_serial_scratch(frWorld *w) {
+    DevWorld &d = w->dw;
+    cudaStream_t s = w->stream;
+    bool ok = true;
+    if (w->lex_cap < d.cap_cand) {
+        const unsigned int cap = d.cap_cand;
+        FxLexScratch &x = w->lex;
+        ok = dev_realloc(x.keys[0], 0, cap, s, false) && dev_realloc(x.keys[1], 0, cap, s, false) &&
+             dev_realloc(x.vals[0], 0, cap, s, false) && dev_realloc(x.vals[1], 0, cap, s, false) &&
+             dev_realloc(x.tmp, 0, cap, s, false);
+        x.dstatus_stride = ((size_t) cap / 2048 + 2) * 256;
+        size_t bytes = 2 * 4 * 256 * sizeof(unsigned int) + 2 * 4 * x.dstatus_stride * sizeof(unsigned int) + 8 * sizeof(unsigned int);
+        if (x.zero_base) { cudaStreamSynchronize(s); cudaFree(x.zero_base); }
+        ok = ok && fx_cuda_ok(cudaMalloc(&x.zero_base, bytes), "cudaMalloc lex");
+        x.zero_bytes = bytes;
+        char *p = (char *) x.zero_base;
+        x.ghist = (unsigned int *) p; p += 2 * 4 * 256 * sizeof(unsigned int);
+        x.dstatus = (unsigned int *) p; p += 2 * 4 * x.dstatus_stride * sizeof(unsigned int);
+        x.tickets = (unsigned int *) p;
+        w->lex_cap = cap;
+    }
+    if (w->so_cap < d.cap_manifolds) {
+        // grow the reference-order key array, keeping its content, and rebuild its index
+        const unsigned int cap = d.cap_manifolds, tcap = pow2_at_least(2ull * cap + 16);
+        const bool first = (w->so.r_len == nullptr);
+        ok = ok && dev_realloc(w->so.r_key, w->so_cap, cap, s, true);
+        if (first) {
+            ok = ok && dev_realloc(w->so.r_len, 0, 1, s, false);
+            cudaMemsetAsync(w->so.r_len, 0, sizeof(unsigned int), s);
+        }
+        ok = ok && dev_realloc(w->so.t_key, 0, tcap, s, false) && dev_realloc(w->so.t_val, 0, tcap, s, false);
+        w->so.t_cap = tcap;
+        cudaMemsetAsync(w->so.t_key, 0xff, (size_t) tcap * sizeof(unsigned long long), s);
+        if (!first) fx_launch_serial_reindex(w->cx, w->so);
+        w->so_cap = cap;
+    }
+    return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the step
+// ---------------------------------------------------------------------------------------------
+static void fill_dev_params(frWorld *w, float dt) {
+    DevWorld &d = w->dw;
+    d.n = (int) w->bodies.size();
+    d.cell = w->cell;
+    d.inv_cell = (w->cell > 0.0f) ? 1.0f / w->cell : 0.0f;     // src/broad_phase.c:62-63
+    d.gx = w->gravity.x;
+    d.gy = w->gravity.y;
+    d.timestamp = w->timestamp;
+    d.dt = dt;
+    d.inv_dt = 1.0f / dt;                                       // src/world.c:242
+    d.solver_mode = w->solver_mode;
+    d.idx_of_uid = w->d_idx_of_uid;
+    d.shapes = w->d_shapes;
+}
+
+static void read_snapshot(frWorld *w, bool wait) {
+    if (!w->snapshot_pending) return;
+    if (wait) cudaEventSynchronize(w->snapshot_ready);
+    else if (cudaEventQuery(w->snapshot_ready) != cudaSuccess) return;
+    w->snapshot_pending = false;
+    w->last = *w->h_snapshot;
+    w->manifold_hint = w->last.n_manifolds;
+    if (w->last.overflow) {
+        w->sticky_overflow |= w->last.overflow;
+        char buf[200];
+        std::snprintf(buf, sizeof buf,
+                      "device buffer overflow in step %lld (mask 0x%x: 1 cell entries, 2 candidates, 4 manifolds, 8 colours, 16 "
+                      "cell-key range); work was dropped",
+                      w->steps, w->last.overflow);
+        fx_set_error(2, buf);
+    }
+}
+
+// Run the broadphase only, read K and C back and size every downstream buffer with head room.
+static bool sizing_prepass(frWorld *w, float dt) {
+    DevWorld &d = w->dw;
+    const unsigned long long n = w->bodies.size();
+    if (!ensure_work_capacity(w, 8 * n + 4096, 16 * n + 4096, 4 * n + 4096)) return false;
+    for (int attempt = 0; attempt < 6; ++attempt) {
+        fill_dev_params(w, dt);
+        fx_launch_begin_step(d, w->cx);
+        if (w->cell > 0.0f && n > 0) fx_launch_broadphase(d, w->cx, false);
+        StepCountersDev c;
+        cudaMemcpyAsync(w->h_snapshot, d.ctr, sizeof c, cudaMemcpyDeviceToHost, w->stream);
+        if (!fx_cuda_ok(cudaStreamSynchronize(w->stream), "sizing pre-pass")) return false;
+        c = *w->h_snapshot;
+        if (c.overflow & 16u) {
+            fx_set_error(3, "world extent exceeds 2^32 broadphase cells (or a body covers > 2^24 cells): enlarge cellSize");
+            return false;
+        }
+        // n_entries / n_cand are clamped to the capacity on overflow: grow and measure again
+        if (c.overflow & 3u) {
+            if (!ensure_work_capacity(w, (c.overflow & 1u) ? 4ull * d.cap_entries : 0, (c.overflow & 2u) ? 4ull * d.cap_cand : 0, 0)) return false;
+            continue;
+        }
+        unsigned long long want_e = 2ull * c.n_entries + 4096, want_c = 2ull * c.n_cand + 4096;
+        unsigned long long want_m = (unsigned long long) c.n_cand + 2ull * w->last.n_manifolds + 4096;
+        if (want_m > want_c) want_m = want_c + w->last.n_manifolds;
+        return ensure_work_capacity(w, want_e, want_c, want_m);
+    }
+    fx_set_error(4, "could not size the broadphase buffers");
+    return false;
+}
+
+static void grow_if_crowded(frWorld *w) {
+    const StepCountersDev &c = w->last;
+    DevWorld &d = w->dw;
+    unsigned long long e = 0, k = 0, m = 0;
+    if (2ull * c.n_entries > d.cap_entries) e = 2ull * d.cap_entries;
+    if (2ull * c.n_cand > d.cap_cand) k = 2ull * d.cap_cand;
+    if (2ull * c.n_manifolds > d.cap_manifolds) m = 2ull * d.cap_manifolds;
+    if (e || k || m) ensure_work_capacity(w, e, k, m);
+}
+
+static void run_handler(frWorld *w, frCollisionEventFunc fn);
+
+static void step_once(frWorld *w, float dt) {
+    DevWorld &d = w->dw;
+    const bool has_handler = (w->handler.preStep != nullptr || w->handler.postStep != nullptr);
+    const bool serial = (w->solver_mode == FRX_SOLVER_SERIAL);
+    const bool collide = (w->cell > 0.0f) && !w->bodies.empty();   // NULL hash: no pairs at all
+
+    ensure_body_capacity(w, (int) w->bodies.size());
+    sync_shapes(w);
+    read_snapshot(w, false);
+    if (w->needs_sizing) {
+        world_push(w);
+        if (!sizing_prepass(w, dt)) return;
+        w->needs_sizing = false;
+    } else {
+        grow_if_crowded(w);
+    }
+    if (serial && !ensure_serial_scratch(w)) return;
+    world_push(w);
+    fill_dev_params(w, dt);
+
+    fx_launch_begin_step(d, w->cx);
+    if (serial && w->lex.zero_base) cudaMemsetAsync(w->lex.zero_base, 0, w->lex.zero_bytes, w->stream);
+    if (collide) {
+        fx_launch_broadphase(d, w->cx, !has_handler);
+        if (serial) {
+            int bits = 1;
+            while ((1ll << bits) < (long long) w->bodies.size() + 1) ++bits;
+            fx_launch_lexsort_candidates(d, w->cx, w->lex, bits);
+        }
+        fx_launch_narrowphase(d, w->cx);
+    } else if (!has_handler) {
+        fx_launch_integrate_velocity(d, w->cx);
+    }
+    fx_launch_cache_update(d, w->cx);
+    if (serial) fx_launch_serial_order(d, w->cx, w->so);
+    if (has_handler) {
+        w->device_newer = true;
+        if (w->handler.preStep) run_handler(w, w->handler.preStep);      // src/world.c:209-214
+        world_push(w);                                                    // setters called by the handler
+        fx_launch_integrate_velocity(d, w->cx);                           // src/world.c:216-220
+    }
+    if (serial) fx_launch_solve_serial_with(d, w->cx, w->so, FR_WORLD_ITERATION_COUNT);
+    else {
+        long long hint = w->manifold_hint > (long long) w->bodies.size() ? w->manifold_hint : (long long) w->bodies.size();
+        fx_launch_solve_colored(d, w->cx, FR_WORLD_ITERATION_COUNT, hint);
+    }
+    fx_launch_integrate_position(d, w->cx);
+    w->device_newer = true;
+    if (has_handler && w->handler.postStep) run_handler(w, w->handler.postStep);   // src/world.c:254-259
+    if (has_handler) world_push(w);
+    fx_launch_finish_step(d, w->cx, w->d_snapshot);
+    cudaMemcpyAsync(w->h_snapshot, w->d_snapshot, sizeof(StepCountersDev), cudaMemcpyDeviceToHost, w->stream);
+    cudaEventRecord(w->snapshot_ready, w->stream);
+    w->snapshot_pending = true;
+    w->steps++;
+    fx_cuda_ok(cudaGetLastError(), "step launch");
+
+    // frPostStepWorld: queue drain (forces were cleared by the position kernel)
+    if (!w->uid_pending_free.empty()) {
+        // uids freed before this step are recyclable now: their cache entries were dropped by it
+        w->uid_free.insert(w->uid_free.end(), w->uid_pending_free.begin(), w->uid_pending_free.end());
+        w->uid_pending_free.clear();
+    }
+    if (w->ring_head != w->ring_tail) drain_queue(w);
+}
+
+extern "C" void frStepWorld(frWorld *w, float dt) {
+    if (w == nullptr || dt <= 0.0f) return;
+    if (!w->device_ok) {
+        fx_set_error(1, "frStepWorld: world has no CUDA device (no CPU fallback)");
+        return;
+    }
+    cudaSetDevice(w->device);
+    step_once(w, dt);
+}
+
+extern "C" void frxStepWorldN(frWorld *w, float dt, int n) {
+    for (int i = 0; i < n; ++i) frStepWorld(w, dt);
+}
+
+// src/world.c:268-285
+extern "C" void frUpdateWorld(frWorld *w, float dt) {
+    if (w == nullptr || dt <= 0.0f) return;
+    float now = frGetCurrentTime();
+    if (w->timestamp <= 0.0f) {
+        w->timestamp = now;
+        return;
+    }
+    float elapsed = now - w->timestamp;
+    w->timestamp = now, w->accumulator += elapsed;
+    for (; w->accumulator >= dt; w->accumulator -= dt) frStepWorld(w, dt);
+}
+
+extern "C" void frxSynchronizeWorld(frWorld *w) {
+    if (!w || !w->device_ok) return;
+    cudaSetDevice(w->device);
+    fx_cuda_ok(cudaStreamSynchronize(w->stream), "synchronize");
+    read_snapshot(w, true);
+}
+
+extern "C" void frxGetStepCounters(frWorld *w, frxStepCounters *out) {
+    if (!w || !out) return;
+    frxSynchronizeWorld(w);
+    out->bodies = (long long) w->bodies.size();
+    out->cellEntries = w->last.n_entries;
+    out->candidates = w->last.n_cand;
+    out->manifolds = w->last.n_manifolds;
+    out->contacts = w->last.n_contacts;
+    out->colors = w->last.n_colors;
+    out->steps = w->steps;
+    out->overflow = w->sticky_overflow;
+}
+
+// ---------------------------------------------------------------------------------------------
+// manifold download / upload (introspection and the collision-handler bridge)
+// ---------------------------------------------------------------------------------------------
+struct ManifoldHost {
+    std::vector<uint2> key;
+    std::vector<int2> body, meta;
+    std::vector<float4> hdr, geo, imp;
+    std::vector<int> cid;
+    std::vector<unsigned long long> order_keys;
+    unsigned int count = 0;
+    int set = 0;
+};
+
+// `after_finish`: the step has completed (cur_flip already toggled), so the live set is flip ^ 1
+static bool download_manifolds(frWorld *w, ManifoldHost &mh, bool after_finish) {
+    DevWorld &d = w->dw;
+    cudaStream_t s = w->stream;
+    int flip = 0;
+    unsigned int m = 0;
+    cudaMemcpyAsync(&flip, d.cur_flip, sizeof(int), cudaMemcpyDeviceToHost, s);
+    if (after_finish) cudaMemcpyAsync(&m, d.prev_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+    else cudaMemcpyAsync(&m, &d.ctr->n_manifolds, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+    if (!fx_cuda_ok(cudaStreamSynchronize(s), "manifold count")) return false;
+    const int set = after_finish ? (flip ^ 1) : flip;
+    mh.set = set;
+    mh.count = m;
+    if (m == 0 || d.cap_manifolds == 0) { mh.count = 0; return true; }
+    const ManifoldSet &ms = d.man[set];
+    mh.key.resize(m); mh.body.resize(m); mh.meta.resize(m); mh.hdr.resize(m);
+    mh.geo.resize(2 * (size_t) m); mh.imp.resize(2 * (size_t) m); mh.cid.resize(2 * (size_t) m);
+    cudaMemcpyAsync(mh.key.data(), ms.key, m * sizeof(uint2), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(mh.body.data(), ms.body, m * sizeof(int2), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(mh.meta.data(), ms.meta, m * sizeof(int2), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(mh.hdr.data(), ms.hdr, m * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(mh.geo.data(), ms.geo, 2 * (size_t) m * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(mh.imp.data(), ms.imp, 2 * (size_t) m * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(mh.cid.data(), ms.cid, 2 * (size_t) m * sizeof(int), cudaMemcpyDeviceToHost, s);
+    mh.order_keys.clear();
+    if (w->solver_mode == FRX_SOLVER_SERIAL && w->so.r_len) {
+        unsigned int len = 0;
+        cudaMemcpyAsync(&len, w->so.r_len, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
+        cudaStreamSynchronize(s);
+        mh.order_keys.resize(len);
+        if (len) cudaMemcpyAsync(mh.order_keys.data(), w->so.r_key, len * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s);
+    }
+    return fx_cuda_ok(cudaStreamSynchronize(s), "manifold download");
+}
+
+static void manifold_to_pod(const ManifoldHost &mh, unsigned int i, frCollision *c) {
+    std::memset(c, 0, sizeof *c);
+    c->count = mh.meta[i].x;
+    c->direction.x = mh.hdr[i].x; c->direction.y = mh.hdr[i].y;
+    c->friction = mh.hdr[i].z; c->restitution = mh.hdr[i].w;
+    for (int k = 0; k < 2; ++k) {
+        const float4 g = mh.geo[2 * i + k], im = mh.imp[2 * i + k];
+        frContact &ct = c->contacts[k];
+        ct.id = mh.cid[2 * i + k];
+        ct.point.x = g.x; ct.point.y = g.y; ct.depth = g.z; ct.timestamp = g.w;
+        ct.cache.normalMass = im.x; ct.cache.normalScalar = im.y; ct.cache.tangentMass = im.z; ct.cache.tangentScalar = im.w;
+    }
+}
+static void pod_to_manifold(ManifoldHost &mh, unsigned int i, const frCollision *c) {
+    mh.meta[i].x = c->count < 0 ? 0 : (c->count > 2 ? 2 : c->count);
+    mh.hdr[i] = make_float4(c->direction.x, c->direction.y, c->friction, c->restitution);
+    for (int k = 0; k < 2; ++k) {
+        const frContact &ct = c->contacts[k];
+        mh.cid[2 * i + k] = ct.id;
+        mh.geo[2 * i + k] = make_float4(ct.point.x, ct.point.y, ct.depth, ct.timestamp);
+        mh.imp[2 * i + k] = make_float4(ct.cache.normalMass, ct.cache.normalScalar, ct.cache.tangentMass, ct.cache.tangentScalar);
+    }
+}
+
+// visiting order of the dense array: reference array order in serial mode, dense order otherwise
+static void visiting_order(const ManifoldHost &mh, std::vector<unsigned int> &order) {
+    order.clear();
+    if (!mh.order_keys.empty() || mh.count == 0) {
+        std::unordered_map<unsigned long long, unsigned int> pos;
+        pos.reserve(mh.count * 2);
+        for (unsigned int i = 0; i < mh.count; ++i) pos[((unsigned long long) mh.key[i].x << 32) | mh.key[i].y] = i;
+        for (unsigned long long k : mh.order_keys) {
+            auto it = pos.find(k);
+            if (it != pos.end()) order.push_back(it->second);
+        }
+        if (!mh.order_keys.empty()) return;
+    }
+    for (unsigned int i = 0; i < mh.count; ++i) order.push_back(i);
+}
+
+// collision-handler sweep (src/world.c:209-214 / :254-259): every entry with count > 0, in solver
+// order, on the caller's thread; the handler may edit *value and enqueue add/remove requests.
+static void run_handler(frWorld *w, frCollisionEventFunc fn) {
+    ManifoldHost mh;
+    if (!download_manifolds(w, mh, false) || mh.count == 0) return;
+    fx_world_pull(w);   // getters inside the handler must see current state
+    std::vector<unsigned int> order;
+    visiting_order(mh, order);
+    bool edited = false;
+    for (unsigned int i : order) {
+        if (mh.meta[i].x <= 0) continue;
+        frCollision c, before;
+        manifold_to_pod(mh, i, &c);
+        before = c;
+        frBodyPair pair;
+        pair.first = (mh.body[i].x >= 0 && mh.body[i].x < (int) w->bodies.size()) ? w->bodies[mh.body[i].x] : nullptr;
+        pair.second = (mh.body[i].y >= 0 && mh.body[i].y < (int) w->bodies.size()) ? w->bodies[mh.body[i].y] : nullptr;
+        fn(pair, &c);
+        if (std::memcmp(&c, &before, sizeof c) != 0) { pod_to_manifold(mh, i, &c); edited = true; }
+    }
+    if (!edited) return;
+    const ManifoldSet &ms = w->dw.man[mh.set];
+    const size_t m = mh.count;
+    cudaStream_t s = w->stream;
+    cudaMemcpyAsync(ms.meta, mh.meta.data(), m * sizeof(int2), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(ms.hdr, mh.hdr.data(), m * sizeof(float4), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(ms.geo, mh.geo.data(), 2 * m * sizeof(float4), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(ms.imp, mh.imp.data(), 2 * m * sizeof(float4), cudaMemcpyHostToDevice, s);
+    cudaMemcpyAsync(ms.cid, mh.cid.data(), 2 * m * sizeof(int), cudaMemcpyHostToDevice, s);
+    fx_cuda_ok(cudaStreamSynchronize(s), "handler upload");
+}
+
+extern "C" int frxGetManifolds(frWorld *w, frxManifold *out, int max) {
+    if (!w || !w->device_ok) return 0;
+    cudaSetDevice(w->device);
+    ManifoldHost mh;
+    if (!download_manifolds(w, mh, true)) return 0;
+    std::vector<unsigned int> order;
+    visiting_order(mh, order);
+    int n = 0;
+    for (unsigned int i : order) {
+        if (out && n < max) {
+            out[n].first = mh.body[i].x;
+            out[n].second = mh.body[i].y;
+            manifold_to_pod(mh, i, &out[n].value);
+        }
+        ++n;
+    }
+    return n;
+}
+
+extern "C" int frxGetCandidatePairs(frWorld *w, int *out, int max) {
+    if (!w || !w->device_ok) return 0;
+    cudaSetDevice(w->device);
+    frxSynchronizeWorld(w);
+    const unsigned int c = w->last.n_cand;
+    if (!out || max <= 0 || c == 0) return (int) c;
+    std::vector<int2> pairs(c);
+    std::vector<unsigned char> hit(c);
+    cudaMemcpy(pairs.data(), w->dw.cand, c * sizeof(int2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(hit.data(), w->dw.cand_hit, c, cudaMemcpyDeviceToHost);
+    for (unsigned int i = 0; i < c && (int) i < max; ++i) {
+        out[3 * i] = pairs[i].x; out[3 * i + 1] = pairs[i].y; out[3 * i + 2] = hit[i];
+    }
+    return (int) c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// batch state access
+// ---------------------------------------------------------------------------------------------
+extern "C" int frxGetBodyStates(frWorld *w, float *position, float *angle, float *sincos, float *velocity,
+                                float *angularVelocity, float *aabb) {
+    if (!w) return 0;
+    if (w->device_ok) cudaSetDevice(w->device);
+    fx_world_pull(w);
+    const int n = (int) w->bodies.size();
+    for (int i = 0; i < n; ++i) {
+        const float4 p = w->h.posrot[i], v = w->h.vel[i], a = w->h.aabb[i];
+        if (position) { position[2 * i] = p.x; position[2 * i + 1] = p.y; }
+        if (sincos) { sincos[2 * i] = p.z; sincos[2 * i + 1] = p.w; }
+        if (angle) angle[i] = w->h.angle[i];
+        if (velocity) { velocity[2 * i] = v.x; velocity[2 * i + 1] = v.y; }
+        if (angularVelocity) angularVelocity[i] = v.z;
+        if (aabb) { aabb[4 * i] = a.x; aabb[4 * i + 1] = a.y; aabb[4 * i + 2] = a.z; aabb[4 * i + 3] = a.w; }
+    }
+    return n;
+}
+
+extern "C" int frxApplyForces(frWorld *w, const float *force, const float *torque, int n) {
+    if (!w) return 0;
+    fx_world_pull(w);
+    if (n > (int) w->bodies.size()) n = (int) w->bodies.size();
+    for (int i = 0; i < n; ++i) {
+        if (w->bodies[i]->inv_mass <= 0.0f) continue;          // src/rigid_body.c:300
+        float4 &f = w->h.force[i];
+        if (force) { f.x = f.x + force[2 * i]; f.y = f.y + force[2 * i + 1]; }
+        if (torque) f.z += torque[i];
+    }
+    w->dirty |= FX_DIRTY_FORCE;
+    return n;
+}
+
+extern "C" int frxSetBodyVelocities(frWorld *w, const float *velocity, const float *angularVelocity, int n) {
+    if (!w) return 0;
+    fx_world_pull(w);
+    if (n > (int) w->bodies.size()) n = (int) w->bodies.size();
+    for (int i = 0; i < n; ++i) {
+        if (velocity) { w->h.vel[i].x = velocity[2 * i]; w->h.vel[i].y = velocity[2 * i + 1]; }
+        if (angularVelocity) w->h.vel[i].z = angularVelocity[i];
+    }
+    w->dirty |= FX_DIRTY_VEL;
+    return n;
+}
+
+extern "C" int frxCreateBodies(frWorld *w, int n, const int *bodyType, const int *shapeIndex, frShape *const *shapes,
+                               const float *position, const float *angle, frBody **outBodies) {
+    if (!w || n <= 0 || !bodyType || !position) return 0;
+    int accepted = 0;
+    for (int i = 0; i < n; ++i) {
+        frVector2 p = { position[2 * i], position[2 * i + 1] };
+        frShape *s = (shapes && shapeIndex && shapeIndex[i] >= 0) ? shapes[shapeIndex[i]] : nullptr;
+        frBody *b = frCreateBodyFromShape((frBodyType) bodyType[i], p, s);
+        if (!b) { if (outBodies) outBodies[i] = nullptr; continue; }
+        if (angle && angle[i] != 0.0f) frSetBodyAngle(b, angle[i]);
+        if (outBodies) outBodies[i] = b;
+        if (frAddBodyToWorld(w, b)) ++accepted;
+    }
+    return accepted;
+}
+
+// ---------------------------------------------------------------------------------------------
+// single-pair / single-body public entry points: a 2-body scratch world on the device
+// ---------------------------------------------------------------------------------------------
+struct Scratch {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    DevWorld dw{};
+    FxLaunchCtx cx{};
+    ShapeDev *d_shapes = nullptr;
+    int2 *d_pairs = nullptr;
+    Manifold *d_out = nullptr;
+    CollisionPod *d_col = nullptr;
+    int pair_cap = 0;
+    // pinned staging
+    float4 *h4 = nullptr;     // posrot[2] vel[2] mprop[2] force[2] aabb[2]
+    float *hangle = nullptr;
+    int2 *hshape = nullptr;
+    ShapeDev *hshapes = nullptr;
+    CollisionPod *hcol = nullptr;
+    Manifold *hout = nullptr;
+};
+static thread_local Scratch g_scratch;
+
+static Scratch *scratch() {
+    Scratch &s = g_scratch;
+    if (s.ready) { cudaSetDevice(s.device); return &s; }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        fx_set_error(1, "no CUDA device: narrow phase / solver entry points have no CPU fallback");
+        return nullptr;
+    }
+    s.device = current_device() < n ? current_device() : 0;
+    cudaSetDevice(s.device);
+    if (!fx_cuda_ok(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking), "scratch stream")) return nullptr;
+    DevWorld &d = s.dw;
+    cudaMalloc((void **) &d.posrot, 2 * sizeof(float4)); cudaMalloc((void **) &d.vel, 2 * sizeof(float4));
+    cudaMalloc((void **) &d.mprop, 2 * sizeof(float4)); cudaMalloc((void **) &d.force, 2 * sizeof(float4));
+    cudaMalloc((void **) &d.aabb, 2 * sizeof(float4)); cudaMalloc((void **) &d.angle, 2 * sizeof(float));
+    cudaMalloc((void **) &d.shape, 2 * sizeof(int2));
+    cudaMalloc((void **) &s.d_shapes, 2 * sizeof(ShapeDev));
+    cudaMalloc((void **) &s.d_pairs, sizeof(int2)); cudaMalloc((void **) &s.d_out, sizeof(Manifold));
+    cudaMalloc((void **) &s.d_col, sizeof(CollisionPod));
+    cudaMallocHost((void **) &s.h4, 10 * sizeof(float4)); cudaMallocHost((void **) &s.hangle, 2 * sizeof(float));
+    cudaMallocHost((void **) &s.hshape, 2 * sizeof(int2)); cudaMallocHost((void **) &s.hshapes, 2 * sizeof(ShapeDev));
+    cudaMallocHost((void **) &s.hcol, sizeof(CollisionPod)); cudaMallocHost((void **) &s.hout, sizeof(Manifold));
+    d.shapes = s.d_shapes;
+    d.n = 2;
+    s.cx.stream = s.stream;
+    s.cx.max_blocks = 148 * 8;
+    s.ready = fx_cuda_ok(cudaGetLastError(), "scratch init");
+    return s.ready ? &s : nullptr;
+}
+
+static BodyRow current_row(frBody *b) {
+    BodyRow r;
+    if (b->world) {
+        fx_world_pull(b->world);
+        const HostMirror &h = b->world->h;
+        const int i = b->index;
+        r.posrot = h.posrot[i]; r.angle = h.angle[i]; r.vel = h.vel[i]; r.mprop = h.mprop[i]; r.force = h.force[i]; r.aabb = h.aabb[i];
+    } else {
+        r = b->loc;
+    }
+    return r;
+}
+static void store_row(frBody *b, const BodyRow &r, unsigned bits) {
+    if (b->world) {
+        HostMirror &h = b->world->h;
+        const int i = b->index;
+        h.posrot[i] = r.posrot; h.angle[i] = r.angle; h.vel[i] = r.vel; h.aabb[i] = r.aabb;
+        fx_world_mark(b->world, bits);
+    } else {
+        b->loc.posrot = r.posrot; b->loc.angle = r.angle; b->loc.vel = r.vel; b->loc.aabb = r.aabb;
+    }
+}
+
+static bool scratch_upload(Scratch *s, frBody *b1, frBody *b2) {
+    frBody *bs[2] = { b1, b2 };
+    for (int k = 0; k < 2; ++k) {
+        frBody *b = bs[k];
+        if (!b) continue;
+        BodyRow r = current_row(b);
+        s->h4[0 + k] = r.posrot; s->h4[2 + k] = r.vel; s->h4[4 + k] = r.mprop; s->h4[6 + k] = r.force; s->h4[8 + k] = r.aabb;
+        s->hangle[k] = r.angle;
+        if (b->shape) { fill_shape_dev(s->hshapes[k], b->shape); s->hshape[k] = make_int2(k, (int) b->shape->type); }
+        else { std::memset(&s->hshapes[k], 0, sizeof(ShapeDev)); s->hshape[k] = make_int2(-1, 0); }
+    }
+    cudaStream_t st = s->stream;
+    DevWorld &d = s->dw;
+    cudaMemcpyAsync(d.posrot, s->h4 + 0, 2 * sizeof(float4), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.vel, s->h4 + 2, 2 * sizeof(float4), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.mprop, s->h4 + 4, 2 * sizeof(float4), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.force, s->h4 + 6, 2 * sizeof(float4), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.aabb, s->h4 + 8, 2 * sizeof(float4), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.angle, s->hangle, 2 * sizeof(float), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(d.shape, s->hshape, 2 * sizeof(int2), cudaMemcpyHostToDevice, st);
+    cudaMemcpyAsync(s->d_shapes, s->hshapes, 2 * sizeof(ShapeDev), cudaMemcpyHostToDevice, st);
+    return true;
+}
+
+// copy exactly the fields the reference's narrow phase writes (src/collision.c:264-558) into the
+// caller's struct, leaving everything else (cached impulses, ids in the circle cases, timestamps,
+// material) as it was
+static void merge_manifold(const Manifold &m, frCollision *c) {
+    c->direction.x = m.dir.x; c->direction.y = m.dir.y;
+    if (m.has_ids) { c->contacts[0].id = m.id[0]; if (m.count == 2) c->contacts[1].id = m.id[1]; }
+    c->contacts[0].point.x = m.p[0].x; c->contacts[0].point.y = m.p[0].y;
+    c->contacts[0].depth = m.depth[0];
+    if (m.count == 2) {
+        c->contacts[1].point.x = m.p[1].x; c->contacts[1].point.y = m.p[1].y;
+        c->contacts[1].depth = m.depth[1];
+    } else {
+        c->contacts[1] = c->contacts[0];
+    }
+    c->count = m.count;
+}
+
+extern "C" bool frComputeCollision(frBody *b1, frBody *b2, frCollision *collision) {
+    if (b1 == nullptr || b2 == nullptr) return false;
+    Scratch *s = scratch();
+    if (!s) return false;
+    scratch_upload(s, b1, b2);
+    int2 pr = make_int2(0, 1);
+    cudaMemcpyAsync(s->d_pairs, &pr, sizeof pr, cudaMemcpyHostToDevice, s->stream);
+    fx_launch_collide_pairs(s->dw, s->cx, s->d_pairs, 1, s->d_out);
+    cudaMemcpyAsync(s->hout, s->d_out, sizeof(Manifold), cudaMemcpyDeviceToHost, s->stream);
+    if (!fx_cuda_ok(cudaStreamSynchronize(s->stream), "frComputeCollision")) return false;
+    if (s->hout->count <= 0) return false;
+    if (collision != nullptr) merge_manifold(*s->hout, collision);
+    return true;
+}
+
+extern "C" int frxComputeCollisions(frWorld *w, const int *pairs, int nPairs, frCollision *out, int *hit) {
+    if (!w || !w->device_ok || !pairs || nPairs <= 0) return 0;
+    cudaSetDevice(w->device);
+    ensure_body_capacity(w, (int) w->bodies.size());
+    sync_shapes(w);
+    world_push(w);
+    fill_dev_params(w, 1.0f);
+    int2 *d_pairs = nullptr;
+    Manifold *d_out = nullptr;
+    cudaMalloc((void **) &d_pairs, (size_t) nPairs * sizeof(int2));
+    cudaMalloc((void **) &d_out, (size_t) nPairs * sizeof(Manifold));
+    cudaMemcpyAsync(d_pairs, pairs, (size_t) nPairs * sizeof(int2), cudaMemcpyHostToDevice, w->stream);
+    fx_launch_collide_pairs(w->dw, w->cx, d_pairs, nPairs, d_out);
+    std::vector<Manifold> res((size_t) nPairs);
+    cudaMemcpyAsync(res.data(), d_out, (size_t) nPairs * sizeof(Manifold), cudaMemcpyDeviceToHost, w->stream);
+    fx_cuda_ok(cudaStreamSynchronize(w->stream), "frxComputeCollisions");
+    cudaFree(d_pairs);
+    cudaFree(d_out);
+    int hits = 0;
+    for (int i = 0; i < nPairs; ++i) {
+        const bool h = res[i].count > 0;
+        if (hit) hit[i] = h ? 1 : 0;
+        if (h) { ++hits; if (out) merge_manifold(res[i], &out[i]); }
+    }
+    return hits;
+}
+
+static void pair_solve(frBody *b1, frBody *b2, frCollision *collision, int op, float inv_dt) {
+    if (b1 == nullptr || b2 == nullptr || collision == nullptr) return;
+    Scratch *s = scratch();
+    if (!s) return;
+    scratch_upload(s, b1, b2);
+    std::memcpy(s->hcol, collision, sizeof(CollisionPod));
+    cudaMemcpyAsync(s->d_col, s->hcol, sizeof(CollisionPod), cudaMemcpyHostToDevice, s->stream);
+    fx_launch_single_pair_solve(s->dw, s->stream, s->d_col, op, inv_dt);
+    cudaMemcpyAsync(s->hcol, s->d_col, sizeof(CollisionPod), cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(s->h4 + 2, s->dw.vel, 2 * sizeof(float4), cudaMemcpyDeviceToHost, s->stream);
+    if (!fx_cuda_ok(cudaStreamSynchronize(s->stream), "pair solve")) return;
+    std::memcpy(collision, s->hcol, sizeof(CollisionPod));
+    frBody *bs[2] = { b1, b2 };
+    for (int k = 0; k < 2; ++k) {
+        BodyRow r = current_row(bs[k]);
+        r.vel = s->h4[2 + k];
+        store_row(bs[k], r, FX_DIRTY_VEL);
+    }
+}
+extern "C" void frApplyAccumulatedImpulses(frBody *b1, frBody *b2, frCollision *collision) { pair_solve(b1, b2, collision, 0, 0.0f); }
+extern "C" void frResolveCollision(frBody *b1, frBody *b2, frCollision *collision, float inverseDt) {
+    pair_solve(b1, b2, collision, 1, inverseDt);
+}
+
+static void single_body(frBody *b, int op, float dt) {
+    if (b == nullptr || dt <= 0.0f) return;
+    Scratch *s = scratch();
+    if (!s) return;
+    scratch_upload(s, b, nullptr);
+    fx_launch_single_body(s->dw, s->stream, 0, op, dt);
+    cudaMemcpyAsync(s->h4 + 0, s->dw.posrot, sizeof(float4), cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(s->h4 + 2, s->dw.vel, sizeof(float4), cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(s->h4 + 8, s->dw.aabb, sizeof(float4), cudaMemcpyDeviceToHost, s->stream);
+    cudaMemcpyAsync(s->hangle, s->dw.angle, sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (!fx_cuda_ok(cudaStreamSynchronize(s->stream), "single body")) return;
+    BodyRow r = current_row(b);
+    r.posrot = s->h4[0]; r.vel = s->h4[2]; r.aabb = s->h4[8]; r.angle = s->hangle[0];
+    store_row(b, r, FX_DIRTY_POSROT | FX_DIRTY_ANGLE | FX_DIRTY_VEL | FX_DIRTY_AABB);
+}
+extern "C" void frIntegrateForBodyVelocity(frBody *b, float dt) { single_body(b, 0, dt); }
+extern "C" void frIntegrateForBodyPosition(frBody *b, float dt) { single_body(b, 1, dt); }
+
+extern "C" int frxDeviceSinCos(const float *angles, int n, float *outSin, float *outCos) {
+    if (!angles || n <= 0) return 0;
+    Scratch *s = scratch();
+    if (!s) return 0;
+    float *d = nullptr;
+    if (!fx_cuda_ok(cudaMalloc((void **) &d, 3 * (size_t) n * sizeof(float)), "cudaMalloc")) return 0;
+    cudaMemcpyAsync(d, angles, (size_t) n * sizeof(float), cudaMemcpyHostToDevice, s->stream);
+    fx_launch_sincos(d, n, d + n, d + 2 * (size_t) n, s->stream);
+    if (outSin) cudaMemcpyAsync(outSin, d + n, (size_t) n * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (outCos) cudaMemcpyAsync(outCos, d + 2 * (size_t) n, (size_t) n * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    bool ok = fx_cuda_ok(cudaStreamSynchronize(s->stream), "frxDeviceSinCos");
+    cudaFree(d);
+    return ok ? n : 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// world ray cast (reference src/world.c:291-320): query API over the synced host state
+// ---------------------------------------------------------------------------------------------
+struct RayCtx {
+    frWorld *w;
+    frRay ray;
+    frRaycastQueryFunc func;
+    void *ctx;
+};
+static bool ray_cb(frContextNode node) {
+    RayCtx *rc = (RayCtx *) node.ctx;
+    if (node.id < 0 || node.id >= (int) rc->w->bodies.size()) return false;
+    frRaycastHit hit;
+    std::memset(&hit, 0, sizeof hit);
+    if (!frComputeRaycast(rc->w->bodies[node.id], rc->ray, &hit)) return false;
+    rc->func(hit, rc->ctx);
+    return true;
+}
+extern "C" void frComputeWorldRaycast(frWorld *w, frRay ray, frRaycastQueryFunc func, void *userData) {
+    if (w == nullptr || func == nullptr || !(w->cell > 0.0f)) return;
+    fx_world_pull(w);
+    frSpatialHash *sh = frCreateSpatialHash(w->cell);
+    for (int i = 0; i < (int) w->bodies.size(); ++i) frInsertIntoSpatialHash(sh, frGetBodyAABB(w->bodies[i]), i);
+    V2 o = v2(ray.origin.x, ray.origin.y);
+    V2 e = vadd(o, vscale(vunit(v2(ray.direction.x, ray.direction.y)), ray.maxDistance));
+    frAABB box;
+    box.x = fminf(o.x, e.x); box.y = fminf(o.y, e.y);
+    box.width = fabsf(e.x - o.x); box.height = fabsf(e.y - o.y);
+    RayCtx rc = { w, ray, func, userData };
+    frQuerySpatialHash(sh, box, ray_cb, &rc);
+    frReleaseSpatialHash(sh);
+}
