@@ -1,0 +1,341 @@
+#!/usr/bin/env python
+"""bench.py -- body-steps/sec of the ferox world step (frStepWorld, 10 PGS iterations).
+
+Workload (N = 1): BASELINE.json configs[1] -- 65,536 mixed circles + convex polygons (3-8 vertices)
+piled in a walled box, contact-cache warm starting on; settled for --settle steps, then timed.
+N > 1: batched independent worlds -- every rank steps its own replica of that world (different seed)
+on its own GPU with no data-path communication ("weak" scaling); torch.distributed (NCCL) only
+provides the barrier and the max-over-ranks reduction of the timings.
+
+One JSON line on rank 0, see the contract in the task description:
+  value      whole-job body-steps/s, state resident in HBM, per-step CUDA events on the stream the
+             kernels run on, L2 flushed (256 MiB memset, untimed) between steps
+  e2e        same metric through the public ferox.h-level calls with HOST buffers: per step the
+             host applies a force to every body (H2D), calls frStepWorld and reads every body state
+             back (D2H), wall clock around the loop
+  roofline   the dominant kernel (k_solve_colored): SURVEY.md section 8d algorithmic bytes
+             (964 B/manifold + 376 B/contact) / its mean device time, against MEASURED_PEAKS.json
+  cpu_baseline  oracle/step_oracle.c (a port; 1 core) on the same settled state, a few steps
+
+`--impl reference` times the UNMODIFIED reference (oracle/_ref/libferox_ref_70000.so, compiled from
+/root/reference by oracle/Makefile) on the host cores: one world per process on every core.
+"""
+import argparse
+import ctypes as C
+import json
+import multiprocessing as mp
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "body-steps/sec (frStepWorld, 10 PGS iterations)"
+UNIT = "body-steps/s"
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libferox_ref_70000.so")
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--bodies", type=int, default=65536)
+    ap.add_argument("--settle", type=int, default=600)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(n):
+    return "config2: %d mixed circles + convex polygons (3-8 verts) pile + 3 static walls, cell 2.0, dt 1/60" % n
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks (B200_PROFILING.md recipe): sampled DURING the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference arm: unmodified reference, one world per host core
+# ------------------------------------------------------------------------------------------------
+def _ref_worker(args):
+    n_bodies, warmup, steps, seed, q = args
+    from ferox_b200 import capi, scenes
+    lib = capi.load_abi(REF_LIB)
+    spec = scenes.mixed_pile(n_bodies, seed=seed)
+    sc = scenes.Scene(lib, spec)
+    t0 = time.perf_counter()
+    sc.step(1)
+    t_one = time.perf_counter() - t0
+    q.put(("calib", t_one))
+    sc.step(max(0, warmup - 1))
+    t0 = time.perf_counter()
+    sc.step(steps)
+    dt = time.perf_counter() - t0
+    q.put(("done", spec.n, steps, dt))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if not os.path.exists(REF_LIB):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref not built (run __graft_entry__.build() where /root/reference exists)"}))
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    # bounded sample: the reference's query is O(FR_WORLD_MAX_OBJECT_COUNT) per body (~3.6 s per step
+    # at 65,536 bodies).  Calibrate one step; if K+W steps would not finish in ~150 s, every process
+    # steps a slab of the same pile with fewer bodies (throughput per body only rises for smaller
+    # worlds, so this errs in the reference's favour) and the sample says so.
+    n = args.bodies
+    budget = 150.0
+    from ferox_b200 import capi, scenes
+    lib = capi.load_abi(REF_LIB)
+    probe = scenes.Scene(lib, scenes.mixed_pile(n, seed=1234))
+    t0 = time.perf_counter(); probe.step(1); t_one = time.perf_counter() - t0
+    probe.release()
+    total_steps = args.steps + args.warmup
+    sample_n = n
+    if t_one * total_steps > budget:
+        # cost model t ~ n * (a + b * MAX_OBJECT_COUNT): dominated by the fixed 70,000-byte scan per body
+        sample_n = max(1024, int(n * budget / (t_one * total_steps)))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_ref_worker, args=((sample_n, args.warmup, args.steps, 1234 + i, q),)) for i in range(procs)]
+    t_start = time.perf_counter()
+    for p in ps:
+        p.start()
+    done = []
+    while len(done) < procs:
+        msg = q.get()
+        if msg[0] == "done":
+            done.append(msg)
+    for p in ps:
+        p.join()
+    wall = max(d[3] for d in done)
+    bodies = sum(d[1] for d in done)
+    value = bodies * args.steps / wall
+    sample = ("%d processes (one world per host core), each a %d-body world of the config-2 recipe stepped from its "
+              "initial lattice (the reference cannot settle 600 steps in bounded time), %d timed steps; full-size step "
+              "calibrated at %.2f s" % (procs, done[0][1], args.steps, t_one))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args.bodies), "parallelism": "%d host processes" % procs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    sys.stdout.flush()
+    _ = t_start
+
+
+# ------------------------------------------------------------------------------------------------
+# the product arm
+# ------------------------------------------------------------------------------------------------
+def run_b200(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world_size > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    import ferox_b200 as fb
+    from ferox_b200 import scenes
+    L = fb.lib()
+    if L.frxSetDevice(local_rank) != 0:
+        raise SystemExit("no CUDA device %d: the ferox world step has no CPU fallback" % local_rank)
+
+    spec = scenes.mixed_pile(args.bodies, seed=1234 + rank)
+    sc = scenes.Scene(L, spec, prime=False)
+    dt = scenes.DT
+    L.frStepWorld(sc.world, dt)                      # priming step: queued bodies enter the world
+    n = L.frGetBodyCountInWorld(sc.world)
+    assert n == spec.n, (n, spec.n)
+    L.frxStepWorldN(sc.world, dt, args.settle)       # settle the pile (untimed)
+    L.frxSynchronizeWorld(sc.world)
+    fb.check_error(L)
+
+    warm = max(3, args.warmup)
+    L.frxStepWorldN(sc.world, dt, warm)
+    L.frxSynchronizeWorld(sc.world)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    # ---- timed region A: device-resident state, per-step CUDA events, cold L2 ----
+    sampler = ClockSampler(local_rank)
+    ms = np.zeros(args.steps, np.float32)
+    L.frxSetProfiling(sc.world, 1)
+    launches0 = L.frxGetLaunchCount()
+    barrier()
+    sampler.start()
+    L.frxTimedSteps(sc.world, dt, args.steps, 1, ms)
+    clocks = sampler.stop()
+    barrier()
+    launches = L.frxGetLaunchCount() - launches0
+    stage_ms = (C.c_double * 5)()
+    prof_steps = L.frxGetStageTimes(sc.world, stage_ms)
+    L.frxSetProfiling(sc.world, 0)
+    ctr = fb.step_counters(L, sc.world)
+    fb.check_error(L)
+    elapsed_ms = float(ms.sum())
+
+    # back-to-back (warm L2, no per-step bracket) for context
+    L.frxRecordEvent(sc.world, 0)
+    L.frxStepWorldN(sc.world, dt, args.steps)
+    L.frxRecordEvent(sc.world, 1)
+    warm_ms = float(L.frxEventElapsedMs(sc.world, 0, 1))
+
+    # ---- timed region B: end to end through host buffers ----
+    force = np.zeros((n, 2), np.float32)
+    force[:, 0] = 0.01
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    st = fb.body_states(L, sc.world)
+    e2e_steps = max(10, min(args.steps, 100))
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for _ in range(e2e_steps):
+        L.frxApplyForces(sc.world, ptr(force), None, n)            # host -> pinned mirror, H2D in the step
+        L.frStepWorld(sc.world, dt)
+        L.frxGetBodyStates(sc.world, ptr(st["pos"]), ptr(st["angle"]), ptr(st["sincos"]), ptr(st["vel"]),
+                           ptr(st["omega"]), ptr(st["aabb"]))       # D2H + host copy of every body state
+        checksum += float(st["pos"][0, 1])
+    L.frxSynchronizeWorld(sc.world)
+    e2e_s = time.perf_counter() - t0
+    barrier()
+    fb.check_error(L)
+
+    # ---- max over ranks ----
+    if dist is not None:
+        import torch
+        t = torch.tensor([elapsed_ms, warm_ms, e2e_s, stage_ms[3]], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms, warm_ms, e2e_s, solve_ms_total = [float(x) for x in t.tolist()]
+        cnt = torch.tensor([n], dtype=torch.float64, device="cuda")
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        total_bodies = int(cnt.item())
+    else:
+        solve_ms_total = float(stage_ms[3])
+        total_bodies = n
+
+    if rank == 0:
+        value = total_bodies * args.steps / (elapsed_ms * 1e-3)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        M, Q = ctr["manifolds"], ctr["contacts"]
+        solve_bytes = 964.0 * M + 376.0 * Q                      # SURVEY.md section 8d, solve-stage terms
+        solve_ms = solve_ms_total / max(1, prof_steps)
+        achieved = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+        step_bytes = (n * (160 + 2 * 24) + 104 * ctr["cellEntries"] + ctr["candidates"] * (64 + 92) + 1060 * M + 376 * Q)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": warm,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.bodies), "bodies_per_gpu": n, "settle_steps": args.settle,
+                       "solver": "graph-coloured PGS, 10 iterations", "parallelism": "independent worlds, 1 per GPU",
+                       "l2": "flushed between timed steps (256 MiB memset on the step's stream, outside the event bracket)",
+                       "counters": ctr},
+            "value_warm_l2": total_bodies * args.steps / (warm_ms * 1e-3),
+            "stage_ms_per_step": {k: stage_ms[i] / max(1, prof_steps) for i, k in
+                                  enumerate(["broadphase", "narrowphase", "cache", "solve", "integrate"])},
+            "step_algorithmic_GBps": step_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
+            "roofline": {"bound": "hbm", "kernel": "k_solve_colored", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "bytes_per_launch": solve_bytes, "ms_per_launch": solve_ms},
+            "e2e": {"value": total_bodies * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 16),
+                    "d2h_bytes_per_step": int(n * 52), "steps": e2e_steps, "checksum": checksum},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(sc, n)
+        print(json.dumps(line))
+        sys.stdout.flush()
+    barrier()
+    sc.release()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(sc, n):
+    """oracle/step_oracle.c on the settled state the GPU just stepped: a bounded sample of steps."""
+    from oracle import orc
+    ow = orc.OracleWorld.from_scene(sc)
+    ow.step(1)                                   # first step has a cold contact cache
+    steps, t0 = 0, time.perf_counter()
+    while steps < 3 or (time.perf_counter() - t0 < 12.0 and steps < 200):
+        ow.step(1)
+        steps += 1
+    dt = time.perf_counter() - t0
+    c = ow.counters()
+    ow.close()
+    return {"value": n * steps / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "%d steps of the same settled %d-body world in oracle/step_oracle.c (sort-based broadphase, "
+                      "reference arithmetic), 1 thread; counters %s" % (steps, n, c)}
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -58,6 +58,12 @@ EXT_PROTOTYPES = {
     "frxGetManifolds": (I, [P, P, I]),
     "frxComputeCollisions": (I, [P, i32p, I, P, P]),
     "frxDeviceSinCos": (I, [f32p, I, f32p, f32p]),
+    "frxSetProfiling": (None, [P, I]),
+    "frxGetStageTimes": (I, [P, C.POINTER(C.c_double)]),
+    "frxRecordEvent": (None, [P, I]),
+    "frxEventElapsedMs": (F, [P, I, I]),
+    "frxGetLaunchCount": (C.c_longlong, []),
+    "frxTimedSteps": (I, [P, F, I, I, f32p]),
 }
 
 _lib = None

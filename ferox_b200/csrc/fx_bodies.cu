@@ -7,6 +7,7 @@
 // 116 B read + 56 B written per body (+ polygon vertices).
 #include "fx_device.h"
 #include "fx_kernels.h"
+extern long long g_fx_launches;
 #include "fx_narrow.cuh"
 #include "fx_solver.cuh"
 
@@ -94,16 +95,16 @@ static inline int grid_for(long long n, int block, int max_blocks) {
 
 void fx_launch_begin_step(const DevWorld &w, const FxLaunchCtx &cx) {
     cudaMemsetAsync(cx.zero_base, 0, cx.zero_bytes, cx.stream);
-    k_begin_step<<<1, 1, 0, cx.stream>>>(w);
+    k_begin_step<<<1, 1, 0, cx.stream>>>(w); ++g_fx_launches;
 }
 
 void fx_launch_integrate_position(const DevWorld &w, const FxLaunchCtx &cx) {
     if (w.n == 0) return;
-    k_integrate_position<<<grid_for(w.n, BD_BLOCK, cx.max_blocks), BD_BLOCK, 0, cx.stream>>>(w);
+    k_integrate_position<<<grid_for(w.n, BD_BLOCK, cx.max_blocks), BD_BLOCK, 0, cx.stream>>>(w); ++g_fx_launches;
 }
 
 void fx_launch_finish_step(const DevWorld &w, const FxLaunchCtx &cx, StepCountersDev *snapshot) {
-    k_finish_step<<<1, 1, 0, cx.stream>>>(w, snapshot);
+    k_finish_step<<<1, 1, 0, cx.stream>>>(w, snapshot); ++g_fx_launches;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -173,11 +174,11 @@ __global__ void k_sincos(const float *a, int n, float *s, float *c) {
     }
 }
 
-void fx_launch_single_body(const DevWorld &w, cudaStream_t s, int i, int op, float dt) { k_single_body<<<1, 32, 0, s>>>(w, i, op, dt); }
+void fx_launch_single_body(const DevWorld &w, cudaStream_t s, int i, int op, float dt) { k_single_body<<<1, 32, 0, s>>>(w, i, op, dt); ++g_fx_launches; }
 void fx_launch_single_pair_solve(const DevWorld &w, cudaStream_t s, CollisionPod *col, int op, float inv_dt) {
-    k_single_pair_solve<<<1, 32, 0, s>>>(w, col, op, inv_dt);
+    k_single_pair_solve<<<1, 32, 0, s>>>(w, col, op, inv_dt); ++g_fx_launches;
 }
 void fx_launch_sincos(const float *a, int n, float *s, float *c, cudaStream_t st) {
     if (n <= 0) return;
-    k_sincos<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(a, n, s, c);
+    k_sincos<<<grid_for(n, 256, 148 * 8), 256, 0, st>>>(a, n, s, c); ++g_fx_launches;
 }

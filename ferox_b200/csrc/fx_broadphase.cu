@@ -22,6 +22,7 @@
 // histogram, pair emission 8 K + 8 C.
 #include "fx_device.h"
 #include "fx_kernels.h"
+extern long long g_fx_launches;
 #include "fx_scan.cuh"
 
 #define BP_BLOCK 256
@@ -315,8 +316,8 @@ static void launch_sort(const SortJob &job, long long cap, int max_passes, int m
     long long gh = (cap + BP_BLOCK * 8 - 1) / (BP_BLOCK * 8), gp = (cap + SORT_TILE - 1) / SORT_TILE;
     int gridh = (int) (gh < 1 ? 1 : (gh > max_blocks ? max_blocks : gh));
     int gridp = (int) (gp < 1 ? 1 : (gp > max_blocks ? max_blocks : gp));
-    k_sort_hist<<<gridh, BP_BLOCK, 0, s>>>(job);
-    for (int p = 0; p < max_passes; ++p) k_sort_pass<<<gridp, BP_BLOCK, 0, s>>>(job, p);
+    k_sort_hist<<<gridh, BP_BLOCK, 0, s>>>(job); ++g_fx_launches;
+    for (int p = 0; p < max_passes; ++p) { k_sort_pass<<<gridp, BP_BLOCK, 0, s>>>(job, p); ++g_fx_launches; }
 }
 
 // ---- lexicographic (i, j) ordering of the candidate list: serial / parity mode only -------------
@@ -400,23 +401,23 @@ static inline int grid_for(long long n, int block, int max_blocks) {
 
 void fx_launch_integrate_velocity(const DevWorld &w, const FxLaunchCtx &cx) {
     if (w.n == 0) return;
-    k_integrate_velocity<<<grid_for(w.n, BP_BLOCK, cx.max_blocks), BP_BLOCK, 0, cx.stream>>>(w);
+    k_integrate_velocity<<<grid_for(w.n, BP_BLOCK, cx.max_blocks), BP_BLOCK, 0, cx.stream>>>(w); ++g_fx_launches;
 }
 
 void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_velocity) {
     cudaStream_t s = cx.stream;
     const int G = cx.max_blocks;
-    k_body_prepass<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, fuse_velocity ? 1 : 0, cx.status[0], cx.tickets + 0);
-    k_plan<<<1, 1, 0, s>>>(w);
-    k_emit_entries<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w);
-    k_emit_large<<<64, BP_BLOCK, 0, s>>>(w);
+    k_body_prepass<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, fuse_velocity ? 1 : 0, cx.status[0], cx.tickets + 0); ++g_fx_launches;
+    k_plan<<<1, 1, 0, s>>>(w); ++g_fx_launches;
+    k_emit_entries<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w); ++g_fx_launches;
+    k_emit_large<<<64, BP_BLOCK, 0, s>>>(w); ++g_fx_launches;
     SortJob job;
     job.keys[0] = w.keys[0]; job.keys[1] = w.keys[1]; job.vals[0] = w.vals[0]; job.vals[1] = w.vals[1];
     job.n = &w.ctr->n_entries; job.passes_dev = &w.ctr->sort_passes; job.passes = 4;
     job.ghist = cx.sort_hist; job.dstatus = cx.digit_status; job.dstatus_stride = cx.digit_status_stride;
     job.tickets = cx.tickets + 8;
     launch_sort(job, (long long) w.cap_entries, 4, G, s);
-    k_emit_pairs<<<grid_for((long long) w.cap_entries, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);
+    k_emit_pairs<<<grid_for((long long) w.cap_entries, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1); ++g_fx_launches;
 }
 
 // Serial mode: reorder the candidate list into the reference's visiting order (i ascending, then j
@@ -427,11 +428,11 @@ void fx_launch_lexsort_candidates(const DevWorld &w, const FxLaunchCtx &cx, cons
     const int G = cx.max_blocks, passes = (body_bits + 7) / 8;
     const int g = grid_for((long long) w.cap_cand, BP_BLOCK, G);
     for (int round = 0; round < 2; ++round) {
-        if (round == 0) k_lex_init<<<g, BP_BLOCK, 0, s>>>(w, lex.keys[0], lex.vals[0]);
+        if (round == 0) { k_lex_init<<<g, BP_BLOCK, 0, s>>>(w, lex.keys[0], lex.vals[0]); ++g_fx_launches; }
         SortJob job;
         // after `passes` passes the data sits in buffer (passes & 1); round 1 starts from there
         int src = (round == 0) ? 0 : (passes & 1);
-        if (round == 1) k_lex_mid<<<g, BP_BLOCK, 0, s>>>(w, lex.vals[src], lex.keys[src]);
+        if (round == 1) { k_lex_mid<<<g, BP_BLOCK, 0, s>>>(w, lex.vals[src], lex.keys[src]); ++g_fx_launches; }
         job.keys[0] = lex.keys[src]; job.keys[1] = lex.keys[src ^ 1];
         job.vals[0] = lex.vals[src]; job.vals[1] = lex.vals[src ^ 1];
         job.n = &w.ctr->n_cand; job.passes_dev = nullptr; job.passes = (unsigned int) passes;
@@ -440,6 +441,6 @@ void fx_launch_lexsort_candidates(const DevWorld &w, const FxLaunchCtx &cx, cons
         launch_sort(job, (long long) w.cap_cand, passes, G, s);
     }
     const int fin = 0;   // round 0 ends in buffer (passes & 1), round 1 starts there and ends in buffer 0
-    k_lex_gather<<<g, BP_BLOCK, 0, s>>>(w, lex.vals[fin], lex.tmp);
-    k_lex_copy<<<g, BP_BLOCK, 0, s>>>(w, lex.tmp);
+    k_lex_gather<<<g, BP_BLOCK, 0, s>>>(w, lex.vals[fin], lex.tmp); ++g_fx_launches;
+    k_lex_copy<<<g, BP_BLOCK, 0, s>>>(w, lex.tmp); ++g_fx_launches;
 }

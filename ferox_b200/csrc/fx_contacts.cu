@@ -18,6 +18,7 @@
 // 12 B per slot cleared + 12 B per entry.
 #include "fx_device.h"
 #include "fx_kernels.h"
+extern long long g_fx_launches;
 #include "fx_narrow.cuh"
 #include "fx_scan.cuh"
 
@@ -267,20 +268,20 @@ static inline int grid_for(long long n, int block, int max_blocks) {
 }
 
 void fx_launch_rehash_prev(const DevWorld &w, const FxLaunchCtx &cx) {
-    k_hash_build_prev<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, cx.stream>>>(w);
+    k_hash_build_prev<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, cx.stream>>>(w); ++g_fx_launches;
 }
 
 void fx_launch_narrowphase(const DevWorld &w, const FxLaunchCtx &cx) {
     cudaStream_t s = cx.stream;
     cudaMemsetAsync(w.touched, 0, w.cap_manifolds, s);
-    k_narrowphase<<<grid_for((long long) w.cap_cand, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[2], cx.tickets + 6);
+    k_narrowphase<<<grid_for((long long) w.cap_cand, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[2], cx.tickets + 6); ++g_fx_launches;
 }
 
 void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx) {
     cudaStream_t s = cx.stream;
-    k_carry_over<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7);
+    k_carry_over<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7); ++g_fx_launches;
     cudaMemsetAsync(w.h_key, 0xff, (size_t) w.cap_hash * sizeof(unsigned long long), s);
-    k_hash_build<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w);
+    k_hash_build<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w); ++g_fx_launches;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -301,5 +302,5 @@ __global__ void __launch_bounds__(NP_BLOCK) k_collide_pairs(DevWorld w, const in
 
 void fx_launch_collide_pairs(const DevWorld &w, const FxLaunchCtx &cx, const int2 *pairs, int n, Manifold *out) {
     if (n <= 0) return;
-    k_collide_pairs<<<grid_for(n, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, cx.stream>>>(w, pairs, n, out);
+    k_collide_pairs<<<grid_for(n, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, cx.stream>>>(w, pairs, n, out); ++g_fx_launches;
 }

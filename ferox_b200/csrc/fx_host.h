@@ -118,7 +118,17 @@ struct frWorld_ {
     long long steps = 0;
     long long sticky_overflow = 0;
     long long manifold_hint = 0;
+
+    // optional per-stage timing (frxSetProfiling): CUDA events on the world's stream around each
+    // stage of every step; frxGetStageTimes sums the elapsed times
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // FX_STAGES + 1 marks per profiled step
+    size_t prof_used = 0;
+    cudaEvent_t user_events[4] = { nullptr, nullptr, nullptr, nullptr };
 };
+
+enum { FX_STAGE_BROADPHASE = 0, FX_STAGE_NARROWPHASE, FX_STAGE_CACHE, FX_STAGE_SOLVE, FX_STAGE_INTEGRATE, FX_STAGES };
+extern long long g_fx_launches;   // kernels launched by this library (all worlds)
 
 struct frSpatialHash_;
 

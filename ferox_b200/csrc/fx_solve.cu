@@ -28,6 +28,7 @@
 
 #include "fx_device.h"
 #include "fx_kernels.h"
+extern long long g_fx_launches;
 #include "fx_scan.cuh"
 #include "fx_solver.cuh"
 
@@ -408,12 +409,13 @@ void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int itera
     DevWorld wc = w;
     void *args[] = { (void *) &wc, (void *) &iterations };
     cudaLaunchCooperativeKernel((const void *) k_solve_colored, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);
+    ++g_fx_launches;
 }
 
-void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o) { k_serial_reindex<<<1, 32, 0, cx.stream>>>(o); }
+void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o) { k_serial_reindex<<<1, 32, 0, cx.stream>>>(o); ++g_fx_launches; }
 void fx_launch_serial_order(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o) {
-    k_serial_order<<<1, 32, 0, cx.stream>>>(w, o);
+    k_serial_order<<<1, 32, 0, cx.stream>>>(w, o); ++g_fx_launches;
 }
 void fx_launch_solve_serial_with(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, int iterations) {
-    k_solve_serial<<<1, 32, 0, cx.stream>>>(w, o, iterations);
+    k_solve_serial<<<1, 32, 0, cx.stream>>>(w, o, iterations); ++g_fx_launches;
 }

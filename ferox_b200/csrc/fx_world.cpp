@@ -15,6 +15,7 @@
 // ---------------------------------------------------------------------------------------------
 // errors, device selection
 // ---------------------------------------------------------------------------------------------
+long long g_fx_launches = 0;
 static int g_error = 0;
 static char g_error_text[256] = "no error";
 static thread_local int g_device = -1;
@@ -168,6 +169,8 @@ static void world_free_device(frWorld *w) {
     if (h.shape) cudaFreeHost(h.shape);
     if (h.uid) cudaFreeHost(h.uid);
     if (w->snapshot_ready) cudaEventDestroy(w->snapshot_ready);
+    for (cudaEvent_t e : w->prof_events) cudaEventDestroy(e);
+    for (cudaEvent_t e : w->user_events) if (e) cudaEventDestroy(e);
     if (w->stream) cudaStreamDestroy(w->stream);
 }
 
@@ -619,6 +622,16 @@ static void grow_if_crowded(frWorld *w) {
 
 static void run_handler(frWorld *w, frCollisionEventFunc fn);
 
+static void prof_mark(frWorld *w) {
+    if (!w->profiling) return;
+    if (w->prof_used == w->prof_events.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        w->prof_events.push_back(e);
+    }
+    cudaEventRecord(w->prof_events[w->prof_used++], w->stream);
+}
+
 static void step_once(frWorld *w, float dt) {
     DevWorld &d = w->dw;
     const bool has_handler = (w->handler.preStep != nullptr || w->handler.postStep != nullptr);
@@ -639,6 +652,7 @@ static void step_once(frWorld *w, float dt) {
     world_push(w);
     fill_dev_params(w, dt);
 
+    prof_mark(w);
     fx_launch_begin_step(d, w->cx);
     if (serial && w->lex.zero_base) cudaMemsetAsync(w->lex.zero_base, 0, w->lex.zero_bytes, w->stream);
     if (collide) {
@@ -648,12 +662,16 @@ static void step_once(frWorld *w, float dt) {
             while ((1ll << bits) < (long long) w->bodies.size() + 1) ++bits;
             fx_launch_lexsort_candidates(d, w->cx, w->lex, bits);
         }
+        prof_mark(w);
         fx_launch_narrowphase(d, w->cx);
-    } else if (!has_handler) {
-        fx_launch_integrate_velocity(d, w->cx);
+    } else {
+        if (!has_handler) fx_launch_integrate_velocity(d, w->cx);
+        prof_mark(w);
     }
+    prof_mark(w);
     fx_launch_cache_update(d, w->cx);
     if (serial) fx_launch_serial_order(d, w->cx, w->so);
+    prof_mark(w);
     if (has_handler) {
         w->device_newer = true;
         if (w->handler.preStep) run_handler(w, w->handler.preStep);      // src/world.c:209-214
@@ -665,7 +683,9 @@ static void step_once(frWorld *w, float dt) {
         long long hint = w->manifold_hint > (long long) w->bodies.size() ? w->manifold_hint : (long long) w->bodies.size();
         fx_launch_solve_colored(d, w->cx, FR_WORLD_ITERATION_COUNT, hint);
     }
+    prof_mark(w);
     fx_launch_integrate_position(d, w->cx);
+    prof_mark(w);
     w->device_newer = true;
     if (has_handler && w->handler.postStep) run_handler(w, w->handler.postStep);   // src/world.c:254-259
     if (has_handler) world_push(w);
@@ -710,6 +730,72 @@ extern "C" void frUpdateWorld(frWorld *w, float dt) {
     float elapsed = now - w->timestamp;
     w->timestamp = now, w->accumulator += elapsed;
     for (; w->accumulator >= dt; w->accumulator -= dt) frStepWorld(w, dt);
+}
+
+extern "C" void frxSetProfiling(frWorld *w, int on) {
+    if (!w) return;
+    w->profiling = on != 0;
+    w->prof_used = 0;
+}
+// sums, over the steps run since frxSetProfiling(w, 1), the device time of each stage in ms:
+// out[0..4] = broadphase (+ velocity integration), narrow phase, cache update, solve, position
+// integration; returns the number of profiled steps
+extern "C" int frxGetStageTimes(frWorld *w, double *out) {
+    if (!w || !w->device_ok || !out) return 0;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    const size_t per = FX_STAGES + 1, steps = w->prof_used / per;
+    for (int k = 0; k < FX_STAGES; ++k) out[k] = 0.0;
+    for (size_t s = 0; s < steps; ++s)
+        for (int k = 0; k < FX_STAGES; ++k) {
+            float ms = 0.f;
+            cudaEventElapsedTime(&ms, w->prof_events[s * per + k], w->prof_events[s * per + k + 1]);
+            out[k] += ms;
+        }
+    return (int) steps;
+}
+extern "C" void frxRecordEvent(frWorld *w, int slot) {
+    if (!w || !w->device_ok || slot < 0 || slot >= 4) return;
+    cudaSetDevice(w->device);
+    if (!w->user_events[slot]) cudaEventCreate(&w->user_events[slot]);
+    cudaEventRecord(w->user_events[slot], w->stream);
+}
+extern "C" float frxEventElapsedMs(frWorld *w, int from, int to) {
+    if (!w || from < 0 || to < 0 || from >= 4 || to >= 4 || !w->user_events[from] || !w->user_events[to]) return -1.0f;
+    cudaSetDevice(w->device);
+    cudaEventSynchronize(w->user_events[to]);
+    float ms = -1.0f;
+    cudaEventElapsedTime(&ms, w->user_events[from], w->user_events[to]);
+    return ms;
+}
+extern "C" long long frxGetLaunchCount(void) { return g_fx_launches; }
+
+// n steps, each bracketed by its own pair of CUDA events on the world's stream; when flushL2 != 0 a
+// 256 MiB scratch buffer is overwritten before every step (outside the bracket) so that no step
+// starts with its inputs resident in the 126 MB L2.  outMs[n] receives the per-step device times.
+static void *g_flush_buf[16] = { nullptr };
+static const size_t FLUSH_BYTES = 256ull << 20;
+extern "C" int frxTimedSteps(frWorld *w, float dt, int n, int flushL2, float *outMs) {
+    if (!w || !w->device_ok || n <= 0 || dt <= 0.0f) return 0;
+    cudaSetDevice(w->device);
+    void *&buf = g_flush_buf[w->device & 15];
+    if (flushL2 && !buf && !fx_cuda_ok(cudaMalloc(&buf, FLUSH_BYTES), "cudaMalloc L2 flush")) return 0;
+    std::vector<cudaEvent_t> ev(2 * (size_t) n);
+    for (auto &e : ev) cudaEventCreate(&e);
+    for (int k = 0; k < n; ++k) {
+        if (flushL2) cudaMemsetAsync(buf, k & 0xff, FLUSH_BYTES, w->stream);
+        cudaEventRecord(ev[2 * k], w->stream);
+        step_once(w, dt);
+        cudaEventRecord(ev[2 * k + 1], w->stream);
+    }
+    fx_cuda_ok(cudaStreamSynchronize(w->stream), "timed steps");
+    for (int k = 0; k < n; ++k) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]);
+        if (outMs) outMs[k] = ms;
+    }
+    for (auto &e : ev) cudaEventDestroy(e);
+    return n;
 }
 
 extern "C" void frxSynchronizeWorld(frWorld *w) {

@@ -263,6 +263,9 @@ class Scene:
     def __init__(self, lib, spec, prime=True):
         self.lib, self.spec = lib, spec
         self.world = lib.frCreateWorld(capi.Vector2(*spec.gravity), spec.cell)
+        if hasattr(lib, "frxSetWorldCapacity") and spec.n + 1 > 2047:
+            # product only: the reference's capacity is the compile-time FR_WORLD_MAX_OBJECT_COUNT
+            lib.frxSetWorldCapacity(self.world, spec.n + 16)
         self.shapes = [make_shape(lib, s) for s in spec.shapes]
         self.bodies = []
         pending = 0

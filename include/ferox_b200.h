@@ -276,6 +276,21 @@ int frxGetManifolds(frWorld *w, frxManifold *out, int max);
    written only on a hit (like frComputeCollision); hit[i] receives 0/1.  Returns hits. */
 int frxComputeCollisions(frWorld *w, const int *pairs, int nPairs, frCollision *out, int *hit);
 
+/* Measurement hooks.  frxSetProfiling(w, 1) brackets every stage of every following step with CUDA
+   events on the world's stream; frxGetStageTimes sums them into out[5] (ms): broadphase (+ velocity
+   integration), narrow phase, cache update, solve, position integration, and returns the number of
+   profiled steps.  frxRecordEvent / frxEventElapsedMs time arbitrary spans on the same stream
+   (slots 0..3).  frxGetLaunchCount: kernels launched by the library so far (all worlds). */
+void frxSetProfiling(frWorld *w, int on);
+int frxGetStageTimes(frWorld *w, double *outMs5);
+void frxRecordEvent(frWorld *w, int slot);
+float frxEventElapsedMs(frWorld *w, int fromSlot, int toSlot);
+long long frxGetLaunchCount(void);
+/* n frStepWorld calls, each bracketed by its own CUDA-event pair on the world's stream; with flushL2
+   a 256 MiB scratch buffer is overwritten before every step, outside the bracket (cold L2).
+   outMs[n] = per-step device milliseconds.  Returns n. */
+int frxTimedSteps(frWorld *w, float dt, int n, int flushL2, float *outMs);
+
 /* Device sinf/cosf (the glibc 2.39 algorithm restated for the position integrator,
    src/rigid_body.c:234-235): evaluates n angles on the GPU; used by the parity tests. */
 int frxDeviceSinCos(const float *angles, int n, float *outSin, float *outCos);
