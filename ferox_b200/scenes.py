@@ -113,10 +113,17 @@ def _poly_radius(nv):
     return max(0.6, 0.42 / math.cos(math.pi / nv))
 
 
-def mixed_pile(n=65536, seed=1234, width=256.0, pitch=1.7, shared_shapes=False):
+def mixed_pile(n=65536, seed=1234, width=None, pitch=1.7, shared_shapes=False, max_rows=96):
     """n dynamic bodies (50 % circles r=0.5, 50 % jittered regular polygons, 3-8 vertices) on a
-    jittered lattice inside a box made of 3 static rectangles, dropped from rest."""
+    jittered lattice inside a box made of 3 static rectangles, dropped from rest.
+
+    The box is at least 256 units wide and widened so that the lattice has at most `max_rows` rows:
+    the reference's solver (and therefore ours) diverges in piles a few hundred rows deep ([probe]:
+    a 353-row column reaches |omega| > 600 after 1,400 steps on the CPU oracle, a 95-row pile stays
+    at KE/body ~0.5 for 2,000 steps), the same normalised-lever-arm pathology as SURVEY.md finding 3."""
     rng = SplitMix64(seed)
+    if width is None:
+        width = max(256.0, 2.0 + pitch * math.ceil(n / max_rows))
     spec = SceneSpec(name="config2_mixed_pile_%d" % n, cell=2.0)
     per_row = max(1, int((width - 2.0) // pitch))
     n_rows = (n + per_row - 1) // per_row
