@@ -1,0 +1,39 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+
+
+def ref_path(cap=8192):
+    return os.path.join(ROOT, "oracle", "_ref", "libferox_ref_%d.so" % cap)
+
+
+@pytest.fixture(scope="session")
+def ref():
+    """The unmodified reference (oracle/_ref, compiled from /root/reference by oracle/Makefile)."""
+    from ferox_b200 import capi
+    p = ref_path(8192)
+    if not os.path.exists(p):
+        pytest.skip("oracle/_ref not built (needs /root/reference at build time)")
+    return capi.load_abi(p)
+
+
+@pytest.fixture(scope="session")
+def prod():
+    """The product library; loading it needs no GPU, stepping does."""
+    import ferox_b200 as fb
+    return fb.lib()
+
+
+@pytest.fixture(scope="session")
+def gpu(prod):
+    assert prod.frxSetDevice(0) == 0, "no CUDA device: -m gpu tests need one (there is no CPU fallback)"
+    return prod
