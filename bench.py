@@ -224,7 +224,12 @@ def run_b200(args):
     launches0 = L.frxGetLaunchCount()
     barrier()
     sampler.start()
+    ncu_range = os.environ.get("FEROX_NCU_RANGE") == "1"     # `ncu --profile-from-start off` captures only this span
+    if ncu_range:
+        L.frxProfilerRange(1)
     L.frxTimedSteps(sc.world, dt, args.steps, 1, ms)
+    if ncu_range:
+        L.frxProfilerRange(0)
     clocks = sampler.stop()
     barrier()
     launches = L.frxGetLaunchCount() - launches0

@@ -22,7 +22,7 @@ SOLVER_COLORED, SOLVER_SERIAL = 0, 1
 
 class StepCounters(C.Structure):
     _fields_ = [(n, C.c_longlong) for n in
-                ("bodies", "cellEntries", "candidates", "manifolds", "contacts", "colors", "steps", "overflow")]
+                ("bodies", "cellEntries", "candidates", "manifolds", "contacts", "colors", "steps", "overflow", "colorRounds")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -63,6 +63,7 @@ EXT_PROTOTYPES = {
     "frxRecordEvent": (None, [P, I]),
     "frxEventElapsedMs": (F, [P, I, I]),
     "frxGetLaunchCount": (C.c_longlong, []),
+    "frxProfilerRange": (None, [I]),
     "frxTimedSteps": (I, [P, F, I, I, f32p]),
 }
 

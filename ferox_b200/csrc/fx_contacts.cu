@@ -22,7 +22,7 @@ extern long long g_fx_launches;
 #include "fx_narrow.cuh"
 #include "fx_scan.cuh"
 
-#define NP_BLOCK 256
+#define NP_BLOCK 128
 #define HASH_EMPTY 0xffffffffffffffffull
 
 __device__ __forceinline__ unsigned int hash_slot(unsigned long long key, unsigned int mask) {
@@ -60,9 +60,32 @@ __device__ __forceinline__ Xf shfl_xf(Xf t, int src) {
     return r;
 }
 
+// Shape records of the pairs a warp is about to evaluate cooperatively, staged in shared memory.
+// Every lane copies the two records of ITS pair with independent 16-byte loads (so the global/L2
+// latency of 32 pairs overlaps); the warp-cooperative evaluation then reads them at smem latency
+// instead of paying a dependent L2 round trip per pair inside the serial ballot loop.
+struct __align__(16) ShapeStage {
+    ShapeDev s[2];
+};
+
+__device__ __forceinline__ void stage_shape(ShapeDev *dst, const ShapeDev *src) {
+    const float4 *g = reinterpret_cast<const float4 *>(src);
+    float4 *d = reinterpret_cast<float4 *>(dst);
+    float4 h0 = g[0], h1 = g[1];                       // type, nv, radius, friction | restitution, pad
+    d[0] = h0;
+    d[1] = h1;
+    const int nv = __float_as_int(h0.y);
+    if (__float_as_int(h0.x) == FX_SHAPE_POLYGON) {
+        const int q = (nv + 1) >> 1;                   // float4 = two vertices
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k < q) { d[2 + k] = g[2 + k]; d[6 + k] = g[6 + k]; }
+    }
+}
+
 // One warp evaluates the 32 candidates its lanes hold: circle/circle per lane, everything else one
 // pair at a time with the whole warp (ballot work loop).  Returns the lane's own manifold.
-__device__ __forceinline__ void warp_narrowphase(const DevWorld &w, bool valid, int bi, int bj, Manifold &m) {
+__device__ __forceinline__ void warp_narrowphase(const DevWorld &w, ShapeStage *stage, bool valid, int bi, int bj, Manifold &m) {
     m.count = 0;
     m.has_ids = 0;
     int2 si = make_int2(-1, 0), sj = make_int2(-1, 0);
@@ -75,20 +98,27 @@ __device__ __forceinline__ void warp_narrowphase(const DevWorld &w, bool valid, 
     }
     const bool has_shapes = valid && si.x >= 0 && sj.x >= 0;
     const bool cc = has_shapes && si.y == FX_SHAPE_CIRCLE && sj.y == FX_SHAPE_CIRCLE;
+    const unsigned int lane = lane_id();
+    if (has_shapes && !cc) {
+        stage_shape(&stage[lane].s[0], &w.shapes[si.x]);
+        stage_shape(&stage[lane].s[1], &w.shapes[sj.x]);
+    }
     if (cc) collide_circles(w.shapes[si.x].radius, ti, w.shapes[sj.x].radius, tj, m);
+    __syncwarp();
     unsigned int todo = __ballot_sync(0xffffffffu, has_shapes && !cc);
     while (todo) {
         int src = __ffs(todo) - 1;
         todo &= todo - 1u;
-        int a = __shfl_sync(0xffffffffu, si.x, src), b = __shfl_sync(0xffffffffu, sj.x, src);
         Xf ta = shfl_xf(ti, src), tb = shfl_xf(tj, src);
         Manifold mm;
-        warp_collide(&w.shapes[a], ta, &w.shapes[b], tb, mm);
-        if ((int) lane_id() == src) m = mm;
+        warp_collide(&stage[src].s[0], ta, &stage[src].s[1], tb, mm);
+        if ((int) lane == src) m = mm;
     }
+    __syncwarp();
 }
 
 __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned long long *status, unsigned int *ticket) {
+    __shared__ ShapeStage s_stage[NP_BLOCK];
     const unsigned int ncand = w.ctr->n_cand;
     const unsigned int ntiles = (ncand + NP_BLOCK - 1) / NP_BLOCK;
     const int cs = *w.cur_flip;
@@ -101,7 +131,7 @@ __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned l
         const bool valid = c < ncand;
         int2 pr = valid ? w.cand[c] : make_int2(0, 0);
         Manifold m;
-        warp_narrowphase(w, valid, pr.x, pr.y, m);
+        warp_narrowphase(w, &s_stage[(threadIdx.x >> 5) * 32], valid, pr.x, pr.y, m);
         const bool hit = valid && m.count > 0;
 
         // contact-cache probe (hit or miss): src/world.c:347-394
@@ -109,6 +139,7 @@ __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned l
         int old = -1;
         float friction = 0.0f, restitution = 0.0f;
         float lam_n[2] = { 0.0f, 0.0f }, lam_t[2] = { 0.0f, 0.0f };
+        int color = -1;
         if (valid) {
             key = ((unsigned long long) w.uid[pr.x] << 32) | (unsigned long long) w.uid[pr.y];
             old = hash_find(w, key);
@@ -120,7 +151,9 @@ __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned l
                 float4 oh = prev.hdr[old];
                 friction = oh.z;
                 restitution = oh.w;
-                int ocount = prev.meta[old].x;
+                const int2 ometa = prev.meta[old];
+                const int ocount = ometa.x;
+                color = ometa.y;                      // keep last step's colour (validated by the solver)
                 int oid0 = prev.cid[2 * old], oid1 = prev.cid[2 * old + 1];
                 for (int i = 0; i < m.count; ++i) {
                     int oi = -1;
@@ -148,7 +181,7 @@ __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned l
                 cur.key[pos] = make_uint2(w.uid[pr.x], w.uid[pr.y]);
                 cur.body[pos] = pr;
                 cur.hdr[pos] = make_float4(m.dir.x, m.dir.y, friction, restitution);
-                cur.meta[pos] = make_int2(m.count, -1);
+                cur.meta[pos] = make_int2(m.count, color);
                 // contacts[1] of a one-point manifold is a copy taken BEFORE stamping / warm-start
                 // transfer (src/collision.c:292,374,...; src/world.c:362-394): id/point/depth only
                 cur.geo[2 * pos] = make_float4(m.p[0].x, m.p[0].y, m.depth[0], w.timestamp);
@@ -187,12 +220,14 @@ __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned lo
         const unsigned int p = tile * NP_BLOCK + threadIdx.x;
         bool keep = false;
         int2 body = make_int2(-1, -1);
-        int count = 0;
+        int count = 0, color = -1;
         if (p < nprev && !w.touched[p]) {
             uint2 k = prev.key[p];
             body.x = w.idx_of_uid[k.x];
             body.y = w.idx_of_uid[k.y];
-            count = prev.meta[p].x;
+            const int2 pm = prev.meta[p];
+            count = pm.x;
+            color = pm.y;
             keep = body.x >= 0 && body.y >= 0;
             for (int c = 0; c < count && keep; ++c)
                 if (w.timestamp - prev.geo[2 * p + c].w > w.dt) keep = false;
@@ -206,7 +241,7 @@ __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned lo
                 cur.key[pos] = prev.key[p];
                 cur.body[pos] = body;
                 cur.hdr[pos] = prev.hdr[p];
-                cur.meta[pos] = make_int2(count, -1);
+                cur.meta[pos] = make_int2(count, color);
                 cur.geo[2 * pos] = prev.geo[2 * p];
                 cur.geo[2 * pos + 1] = prev.geo[2 * p + 1];
                 cur.imp[2 * pos] = prev.imp[2 * p];
@@ -288,6 +323,7 @@ void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx) {
 // batched stand-alone narrow phase (frComputeCollision / frxComputeCollisions)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NP_BLOCK) k_collide_pairs(DevWorld w, const int2 *pairs, int n, Manifold *out) {
+    __shared__ ShapeStage s_stage[NP_BLOCK];
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (n + stride - 1) / stride;
     for (int r = 0; r < rounds; ++r) {
@@ -295,7 +331,7 @@ __global__ void __launch_bounds__(NP_BLOCK) k_collide_pairs(DevWorld w, const in
         bool valid = c < n;
         int2 pr = valid ? pairs[c] : make_int2(0, 0);
         Manifold m;
-        warp_narrowphase(w, valid, pr.x, pr.y, m);
+        warp_narrowphase(w, &s_stage[(threadIdx.x >> 5) * 32], valid, pr.x, pr.y, m);
         if (valid) out[c] = m;
     }
 }

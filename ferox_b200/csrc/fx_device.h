@@ -136,6 +136,7 @@ struct DevWorld {
     unsigned int *order;                 // manifold indices grouped by colour
     unsigned int *color_off;             // [FX_MAX_COLORS + 1]
     unsigned long long *body_mask;       // colours already used by each body
+    unsigned long long *body_dup;        // colours seen more than once on a body (inherited clashes)
     unsigned int *winner;                // colouring: per-body claim
     int2 *cbody;                         // per manifold: the bodies that constrain its colour (-1: none)
     unsigned int *color_scratch;         // [3][FX_MAX_COLORS]: counts, fill cursors, per-round remaining

@@ -8,6 +8,7 @@ struct FxLaunchCtx {
     cudaStream_t stream;
     int max_blocks;                 // grid cap for grid-stride kernels (multiple of the SM count)
     int coop_blocks;                // co-resident grid of the cooperative solver kernel
+    int num_sms;
     unsigned long long *status[4];  // 0 body prepass, 1 pair emission, 2 narrow phase, 3 carry-over
     size_t status_words[4];
     unsigned int *tickets;          // [16]

@@ -131,16 +131,39 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
     unsigned int *color_cnt = w.color_scratch, *color_fill = w.color_scratch + FX_MAX_COLORS,
                  *color_rem = w.color_scratch + 2 * FX_MAX_COLORS;
 
-    // ---- phase 0: reset per-body colouring state, find the bodies that constrain each manifold
+    // ---- phase 0: per-body colouring state.  Manifolds that persist from the previous step arrive
+    // with the colour they had (carried through the contact cache); those colours are re-validated
+    // here (a body that became dynamic may now see one colour twice) and only new manifolds go
+    // through the greedy rounds below.
     for (unsigned int i = tid; i < (unsigned int) w.n; i += nth) {
         w.body_mask[i] = 0ull;
+        w.body_dup[i] = 0ull;
         w.winner[i] = 0xffffffffu;
     }
+    for (unsigned int i = tid; i < 3 * FX_MAX_COLORS; i += nth) w.color_scratch[i] = 0u;
+    grid.sync();
     for (unsigned int m = tid; m < M; m += nth) {
         int2 b = man.body[m];
-        w.cbody[m] = make_int2(body_is_written(w, b.x) ? b.x : -1, body_is_written(w, b.y) ? b.y : -1);
+        int2 cb = make_int2(body_is_written(w, b.x) ? b.x : -1, body_is_written(w, b.y) ? b.y : -1);
+        w.cbody[m] = cb;
+        const int col = man.meta[m].y;
+        if (col >= 0) {
+            const unsigned long long bit = 1ull << col;
+            if (cb.x >= 0 && (atomicOr(&w.body_mask[cb.x], bit) & bit)) atomicOr(&w.body_dup[cb.x], bit);
+            if (cb.y >= 0 && (atomicOr(&w.body_mask[cb.y], bit) & bit)) atomicOr(&w.body_dup[cb.y], bit);
+        }
     }
-    for (unsigned int i = tid; i < 3 * FX_MAX_COLORS; i += nth) w.color_scratch[i] = 0u;
+    grid.sync();
+    for (unsigned int m = tid; m < M; m += nth) {
+        int2 meta = man.meta[m];
+        if (meta.y < 0) continue;
+        const unsigned long long bit = 1ull << meta.y;
+        const int2 cb = w.cbody[m];
+        if ((cb.x >= 0 && (w.body_dup[cb.x] & bit)) || (cb.y >= 0 && (w.body_dup[cb.y] & bit))) {
+            meta.y = -1;                              // every manifold of a clash is recoloured
+            man.meta[m] = meta;
+        }
+    }
     grid.sync();
 
     // ---- phase 1: colouring rounds
@@ -171,7 +194,7 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
         }
         if (left) atomicAdd(&color_rem[round], left);
         grid.sync();
-        if (color_rem[round] == 0u) break;
+        if (color_rem[round] == 0u) { if (tid == 0) w.ctr->uncolored = round + 1u; break; }
     }
 
     // ---- phase 2: counting sort of manifold indices by colour
@@ -218,12 +241,14 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
     // ---- phase 3: solver records + warm start, one colour at a time
     const unsigned int ncolors = s_ncolors;
     for (unsigned int c = 0; c < ncolors; ++c) {
+        if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
         for (unsigned int s = s_off[c] + tid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s);
         grid.sync();
     }
     // ---- phase 4: Gauss-Seidel sweeps
     for (int it = 0; it < iterations; ++it)
         for (unsigned int c = 0; c < ncolors; ++c) {
+            if (s_off[c] == s_off[c + 1]) continue;
             for (unsigned int s = s_off[c] + tid; s < s_off[c + 1]; s += nth) sweep_one(w, s);
             grid.sync();
         }
@@ -404,8 +429,16 @@ int fx_query_coop_blocks(int device) {
 }
 
 void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint) {
-    long long want = (work_hint + SV_BLOCK - 1) / SV_BLOCK;
-    int blocks = (int) (want < 1 ? 1 : (want > cx.coop_blocks ? cx.coop_blocks : want));
+    // A phase holds ~1/8 of the manifolds (one colour).  Fewer resident blocks make the ~100 grid
+    // barriers of a solve cheaper, so take just enough blocks to give every manifold of a phase its
+    // own thread, in whole multiples of the SM count, at least one block per SM.
+    long long want = (work_hint / 6 + SV_BLOCK - 1) / SV_BLOCK;
+    int per_sm = cx.coop_blocks / (cx.num_sms > 0 ? cx.num_sms : 1);
+    long long k = (want + cx.num_sms - 1) / cx.num_sms;
+    if (k < 1) k = 1;
+    if (k > per_sm) k = per_sm;
+    int blocks = (int) (k * cx.num_sms);
+    if (work_hint <= 2048) blocks = (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK) < 1 ? 1 : (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK);
     DevWorld wc = w;
     void *args[] = { (void *) &wc, (void *) &iterations };
     cudaLaunchCooperativeKernel((const void *) k_solve_colored, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);

@@ -10,6 +10,8 @@
 #include <cstring>
 #include <new>
 
+#include <cuda_profiler_api.h>
+
 #include "fx_host.h"
 
 // ---------------------------------------------------------------------------------------------
@@ -105,6 +107,7 @@ static bool world_device_init(frWorld *w) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, w->device);
     w->cx.stream = w->stream;
     w->cx.max_blocks = sms * 8;
+    w->cx.num_sms = sms;
     w->cx.coop_blocks = fx_query_coop_blocks(w->device);
     fx_cuda_ok(cudaMalloc((void **) &w->d_snapshot, sizeof(StepCountersDev)), "cudaMalloc");
     fx_cuda_ok(cudaMallocHost((void **) &w->h_snapshot, sizeof(StepCountersDev)), "cudaMallocHost");
@@ -151,7 +154,7 @@ static void world_free_device(frWorld *w) {
     cudaFree(d.touched); cudaFree(d.h_key); cudaFree(d.h_val);
     cudaFree(d.sol.body); cudaFree(d.sol.nt); cudaFree(d.sol.mat); cudaFree(d.sol.count_src);
     cudaFree(d.sol.r); cudaFree(d.sol.u); cudaFree(d.sol.k); cudaFree(d.sol.lam);
-    cudaFree(d.order); cudaFree(d.color_off); cudaFree(d.body_mask); cudaFree(d.winner); cudaFree(d.cbody);
+    cudaFree(d.order); cudaFree(d.color_off); cudaFree(d.body_mask); cudaFree(d.body_dup); cudaFree(d.winner); cudaFree(d.cbody);
     cudaFree(d.color_scratch); cudaFree(d.ctr); cudaFree(d.prev_count); cudaFree(d.cur_flip);
     cudaFree(w->cx.zero_base);
     cudaFree(w->lex.keys[0]); cudaFree(w->lex.keys[1]); cudaFree(w->lex.vals[0]); cudaFree(w->lex.vals[1]);
@@ -258,7 +261,7 @@ static bool ensure_body_capacity(frWorld *w, int need) {
          dev_realloc(d.force, o, n, s, true) && dev_realloc(d.aabb, o, n, s, true) && dev_realloc(d.angle, o, n, s, true) &&
          dev_realloc(d.shape, o, n, s, true) && dev_realloc(d.uid, o, n, s, true) &&
          dev_realloc(d.cell_cnt, 0, n, s, false) && dev_realloc(d.cell_off, 0, n, s, false) &&
-         dev_realloc(d.large_list, 0, n, s, false) && dev_realloc(d.body_mask, 0, n, s, false) &&
+         dev_realloc(d.large_list, 0, n, s, false) && dev_realloc(d.body_mask, 0, n, s, false) && dev_realloc(d.body_dup, 0, n, s, false) &&
          dev_realloc(d.winner, 0, n, s, false);
     d.cap_large = (unsigned int) n;
     w->body_cap = cap;
@@ -446,7 +449,7 @@ static bool rebuild_zero_region(frWorld *w) {
     DevWorld &d = w->dw;
     FxLaunchCtx &cx = w->cx;
     size_t tiles_body = (size_t) w->body_cap / 256 + 2, tiles_ent = (size_t) d.cap_entries / 256 + 2;
-    size_t tiles_cand = (size_t) d.cap_cand / 256 + 2, tiles_man = (size_t) d.cap_manifolds / 256 + 2;
+    size_t tiles_cand = (size_t) d.cap_cand / 128 + 2, tiles_man = (size_t) d.cap_manifolds / 128 + 2;
     size_t sort_tiles = (size_t) d.cap_entries / 2048 + 2;
     cx.status_words[0] = tiles_body; cx.status_words[1] = tiles_ent; cx.status_words[2] = tiles_cand; cx.status_words[3] = tiles_man;
     cx.digit_status_stride = sort_tiles * 256;
@@ -769,6 +772,7 @@ extern "C" float frxEventElapsedMs(frWorld *w, int from, int to) {
     return ms;
 }
 extern "C" long long frxGetLaunchCount(void) { return g_fx_launches; }
+extern "C" void frxProfilerRange(int start) { if (start) cudaProfilerStart(); else cudaProfilerStop(); }
 
 // n steps, each bracketed by its own pair of CUDA events on the world's stream; when flushL2 != 0 a
 // 256 MiB scratch buffer is overwritten before every step (outside the bracket) so that no step
@@ -814,6 +818,7 @@ extern "C" void frxGetStepCounters(frWorld *w, frxStepCounters *out) {
     out->manifolds = w->last.n_manifolds;
     out->contacts = w->last.n_contacts;
     out->colors = w->last.n_colors;
+    out->colorRounds = w->last.uncolored;
     out->steps = w->steps;
     out->overflow = w->sticky_overflow;
 }

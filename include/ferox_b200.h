@@ -217,6 +217,7 @@ typedef struct frxStepCounters_ {
     long long colors;      /* colours used by the solver (0 in serial mode)         */
     long long steps;       /* frStepWorld calls completed on this world             */
     long long overflow;    /* != 0: a device buffer overflowed (work was dropped)   */
+    long long colorRounds; /* rounds the greedy colouring needed                    */
 } frxStepCounters;
 
 /* CUDA device selection for worlds created afterwards by this thread (default: device 0, or the
@@ -286,6 +287,8 @@ int frxGetStageTimes(frWorld *w, double *outMs5);
 void frxRecordEvent(frWorld *w, int slot);
 float frxEventElapsedMs(frWorld *w, int fromSlot, int toSlot);
 long long frxGetLaunchCount(void);
+/* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture a span */
+void frxProfilerRange(int start);
 /* n frStepWorld calls, each bracketed by its own CUDA-event pair on the world's stream; with flushL2
    a 256 MiB scratch buffer is overwritten before every step, outside the bracket (cold L2).
    outMs[n] = per-step device milliseconds.  Returns n. */
