@@ -83,8 +83,11 @@ __device__ __forceinline__ void stage_shape(ShapeDev *dst, const ShapeDev *src) 
     }
 }
 
-// One warp evaluates the 32 candidates its lanes hold: circle/circle per lane, everything else one
-// pair at a time with the whole warp (ballot work loop).  Returns the lane's own manifold.
+// One warp evaluates the 32 candidates its lanes hold: circle/circle per lane; every other pair by
+// a group of 8 lanes (one lane per polygon axis), four pairs at a time, polygon/polygon pairs and
+// circle/polygon pairs in separate sweeps so the four groups of a sweep run the same code.  A
+// group's result is handed to the lane that owns the candidate through that lane's (now consumed)
+// shape-stage slot.  Returns the lane's own manifold.
 __device__ __forceinline__ void warp_narrowphase(const DevWorld &w, ShapeStage *stage, bool valid, int bi, int bj, Manifold &m) {
     m.count = 0;
     m.has_ids = 0;
@@ -98,27 +101,74 @@ __device__ __forceinline__ void warp_narrowphase(const DevWorld &w, ShapeStage *
     }
     const bool has_shapes = valid && si.x >= 0 && sj.x >= 0;
     const bool cc = has_shapes && si.y == FX_SHAPE_CIRCLE && sj.y == FX_SHAPE_CIRCLE;
+    const bool pp = has_shapes && si.y == FX_SHAPE_POLYGON && sj.y == FX_SHAPE_POLYGON;
     const unsigned int lane = lane_id();
+    const int grp = (int) (lane >> 3), k = (int) (lane & 7u);
+    const unsigned int gmask = 0xffu << (lane & 24u);
     if (has_shapes && !cc) {
         stage_shape(&stage[lane].s[0], &w.shapes[si.x]);
         stage_shape(&stage[lane].s[1], &w.shapes[sj.x]);
     }
     if (cc) collide_circles(w.shapes[si.x].radius, ti, w.shapes[sj.x].radius, tj, m);
     __syncwarp();
-    unsigned int todo = __ballot_sync(0xffffffffu, has_shapes && !cc);
-    while (todo) {
-        int src = __ffs(todo) - 1;
-        todo &= todo - 1u;
-        Xf ta = shfl_xf(ti, src), tb = shfl_xf(tj, src);
-        Manifold mm;
-        warp_collide(&stage[src].s[0], ta, &stage[src].s[1], tb, mm);
-        if ((int) lane == src) m = mm;
+    const unsigned int all_pp = __ballot_sync(0xffffffffu, pp);
+    const unsigned int all_other = __ballot_sync(0xffffffffu, has_shapes && !cc && !pp);
+#pragma unroll 1
+    for (int sweep = 0; sweep < 2; ++sweep) {
+        unsigned int todo = sweep == 0 ? all_pp : all_other;
+        while (todo) {
+            // the next (up to) four candidates, one per group
+            int src = -1;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                int f = todo ? __ffs(todo) - 1 : -1;
+                if (todo) todo &= todo - 1u;
+                if (g == grp) src = f;
+            }
+            const int from = src >= 0 ? src : 0;
+            Xf ta = shfl_xf(ti, from), tb = shfl_xf(tj, from);
+            if (src >= 0) {
+                Manifold mm;
+                grp_collide(gmask, k, &stage[src].s[0], ta, &stage[src].s[1], tb, mm);
+                __syncwarp(gmask);
+                if (k == 0) *reinterpret_cast<Manifold *>(&stage[src]) = mm;
+            }
+        }
     }
+    __syncwarp();
+    if (has_shapes && !cc) m = *reinterpret_cast<const Manifold *>(&stage[lane]);
     __syncwarp();
 }
 
+// Lane-per-pair variant (default): every lane evaluates its own candidate with the reference's
+// loops; polygon data staged per lane in shared memory (LaneShapes, 8 KB per warp).
+__device__ __forceinline__ void lane_narrowphase(const DevWorld &w, LaneShapes *sh, bool valid, int bi, int bj, Manifold &m) {
+    m.count = 0;
+    m.has_ids = 0;
+    if (!valid) return;
+    const int2 si = w.shape[bi], sj = w.shape[bj];
+    if (si.x < 0 || sj.x < 0) return;
+    const Xf ti = load_xf(w, bi), tj = load_xf(w, bj);
+    const ShapeDev *ga = &w.shapes[si.x], *gb = &w.shapes[sj.x];
+    const int lane = (int) lane_id();
+    const float4 ha = *reinterpret_cast<const float4 *>(ga), hb = *reinterpret_cast<const float4 *>(gb);
+    const int ta = __float_as_int(ha.x), tb = __float_as_int(hb.x);     // live shape types
+    LanePoly pa = { sh, 0, lane, __float_as_int(ha.y) }, pb = { sh, 1, lane, __float_as_int(hb.y) };
+    if (ta == FX_SHAPE_POLYGON) lane_stage_poly(sh, 0, lane, ga, pa.nv);
+    if (tb == FX_SHAPE_POLYGON) lane_stage_poly(sh, 1, lane, gb, pb.nv);
+    if (ta == FX_SHAPE_CIRCLE && tb == FX_SHAPE_CIRCLE) collide_circles(ha.z, ti, hb.z, tj, m);
+    else if (ta == FX_SHAPE_CIRCLE && tb == FX_SHAPE_POLYGON) lane_collide_circle_poly(true, ha.z, pb, ti, tj, m);
+    else if (ta == FX_SHAPE_POLYGON && tb == FX_SHAPE_CIRCLE) lane_collide_circle_poly(false, hb.z, pa, ti, tj, m);
+    else if (ta == FX_SHAPE_POLYGON && tb == FX_SHAPE_POLYGON) lane_collide_polys(pa, ti, pb, tj, m);
+}
+
+union NarrowStage {
+    ShapeStage group[NP_BLOCK];                 // 8-lanes-per-pair variant
+    LaneShapes lane[NP_BLOCK / 32];             // lane-per-pair variant
+};
+
 __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned long long *status, unsigned int *ticket) {
-    __shared__ ShapeStage s_stage[NP_BLOCK];
+    __shared__ NarrowStage s_stage;
     const unsigned int ncand = w.ctr->n_cand;
     const unsigned int ntiles = (ncand + NP_BLOCK - 1) / NP_BLOCK;
     const int cs = *w.cur_flip;
@@ -131,7 +181,8 @@ __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned l
         const bool valid = c < ncand;
         int2 pr = valid ? w.cand[c] : make_int2(0, 0);
         Manifold m;
-        warp_narrowphase(w, &s_stage[(threadIdx.x >> 5) * 32], valid, pr.x, pr.y, m);
+        if (w.narrow_mode == 0) lane_narrowphase(w, &s_stage.lane[threadIdx.x >> 5], valid, pr.x, pr.y, m);
+        else warp_narrowphase(w, &s_stage.group[(threadIdx.x >> 5) * 32], valid, pr.x, pr.y, m);
         const bool hit = valid && m.count > 0;
 
         // contact-cache probe (hit or miss): src/world.c:347-394
@@ -323,7 +374,7 @@ void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx) {
 // batched stand-alone narrow phase (frComputeCollision / frxComputeCollisions)
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NP_BLOCK) k_collide_pairs(DevWorld w, const int2 *pairs, int n, Manifold *out) {
-    __shared__ ShapeStage s_stage[NP_BLOCK];
+    __shared__ NarrowStage s_stage;
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (n + stride - 1) / stride;
     for (int r = 0; r < rounds; ++r) {
@@ -331,7 +382,8 @@ __global__ void __launch_bounds__(NP_BLOCK) k_collide_pairs(DevWorld w, const in
         bool valid = c < n;
         int2 pr = valid ? pairs[c] : make_int2(0, 0);
         Manifold m;
-        warp_narrowphase(w, &s_stage[(threadIdx.x >> 5) * 32], valid, pr.x, pr.y, m);
+        if (w.narrow_mode == 0) lane_narrowphase(w, &s_stage.lane[threadIdx.x >> 5], valid, pr.x, pr.y, m);
+        else warp_narrowphase(w, &s_stage.group[(threadIdx.x >> 5) * 32], valid, pr.x, pr.y, m);
         if (valid) out[c] = m;
     }
 }

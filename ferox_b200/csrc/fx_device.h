@@ -108,6 +108,7 @@ struct DevWorld {
     float timestamp;
     float dt, inv_dt;
     int solver_mode;
+    int narrow_mode;     // 0: one lane per pair (default), 1: 8 lanes per pair with shuffle arg-max over axes
     // bodies
     float4 *posrot, *vel, *mprop, *force, *aabb;
     float *angle;

@@ -2,12 +2,14 @@
 // polygon/polygon SAT + clipping.  Replaces reference src/collision.c:114-135, 228-558, 628-724.
 //
 // Execution shape: circle/circle pairs are one thread each.  Every pair that involves a polygon is
-// evaluated by a whole warp: the <= 8 x 8 (axis, vertex) dot products of a SAT direction sit one
-// (axis, vertex-pair) per lane and the two arg-max searches (support vertex per axis, then the axis
-// of least penetration) are shuffle reductions.  The reductions keep the reference's tie rule
-// ("first maximum wins": strict `<` in index order, src/collision.c:697,718) by preferring the lower
-// index among equal values, so feature ids stay bit-exact.  The short scalar tail (edge selection,
-// clipping) is computed redundantly by all lanes, i.e. without divergence.
+// evaluated cooperatively by a group of 8 lanes, ONE LANE PER POLYGON AXIS (FR_GEOMETRY_MAX_VERTEX_COUNT
+// = 8), four pairs per warp: each lane walks the <= 8 vertices of the other polygon for its axis (the
+// support search, sequential so "first maximum wins" holds by construction, src/collision.c:718) and
+// the axis of least penetration is a 3-step shuffle arg-max across the group that prefers the lower
+// index among equal depths (the reference's strict `<`, src/collision.c:697), so feature ids stay
+// bit-exact.  The short scalar tail (edge selection, clipping) is computed redundantly by the 8
+// lanes.  [measured, profiles/r01: a whole warp per pair (32 lanes, 2 vertices per lane) issued
+// ~4x more warp instructions per pair and ran the 65k-body narrow phase in 248 us.]
 #pragma once
 #include "fx_device.h"
 #include "fx_scan.cuh"
@@ -28,11 +30,18 @@ FX_D ArgMax am_best(ArgMax a, ArgMax b) {
     bool take_b = (b.v > a.v) || (b.v == a.v && b.i < a.i);
     return take_b ? b : a;
 }
-FX_D ArgMax am_shfl_xor(ArgMax a, int d) {
+FX_D ArgMax am_shfl_xor(unsigned int mask, ArgMax a, int d) {
     ArgMax b;
-    b.v = __shfl_xor_sync(0xffffffffu, a.v, d);
-    b.i = __shfl_xor_sync(0xffffffffu, a.i, d);
+    b.v = __shfl_xor_sync(mask, a.v, d);
+    b.i = __shfl_xor_sync(mask, a.i, d);
     return am_best(a, b);
+}
+// arg-max over the 8 lanes of a group (mask names exactly those lanes)
+FX_D ArgMax am_group8(unsigned int mask, ArgMax a) {
+    a = am_shfl_xor(mask, a, 1);
+    a = am_shfl_xor(mask, a, 2);
+    a = am_shfl_xor(mask, a, 4);
+    return a;
 }
 
 // circle vs circle, src/collision.c:264-298 (one thread)
@@ -54,25 +63,22 @@ FX_D void collide_circles(float r1, Xf t1, float r2, Xf t2, Manifold &m) {
     m.count = 1;
 }
 
-// circle vs polygon in either order, src/collision.c:305-449.  Warp-cooperative: all 32 lanes call
-// this with identical arguments and receive identical results.
-FX_D void warp_collide_circle_poly(const ShapeDev *s1, Xf t1, const ShapeDev *s2, Xf t2, Manifold &m) {
+// circle vs polygon in either order, src/collision.c:305-449.  Group-cooperative: the 8 lanes named
+// by `gmask` call this with identical arguments and receive identical results; k = lane within group.
+FX_D void grp_collide_circle_poly(unsigned int gmask, int k, const ShapeDev *s1, Xf t1, const ShapeDev *s2, Xf t2, Manifold &m) {
     m.count = 0;
     m.has_ids = 0;
     const bool first_is_circle = (s1->type == FX_SHAPE_CIRCLE);
     const ShapeDev *circle = first_is_circle ? s1 : s2, *poly = first_is_circle ? s2 : s1;
     const Xf ct = first_is_circle ? t1 : t2, pt = first_is_circle ? t2 : t1;
     const int nv = poly->nv;
-    const unsigned int lane = lane_id();
 
     V2 c = xf_unrotate(vsub(ct.p, pt.p), pt);          // circle centre in polygon space (:328-330)
     const float radius = circle->radius;
     float dot = -INFINITY;
-    if ((int) lane < nv) dot = vdot(poly->normals[lane], vsub(c, poly->verts[lane]));
-    if (__any_sync(0xffffffffu, (int) lane < nv && dot > radius)) return;   // separating face (:345)
-    ArgMax best = am_make(dot, (int) lane, (int) lane < nv);
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) best = am_shfl_xor(best, d);
+    if (k < nv) dot = vdot(poly->normals[k], vsub(c, poly->verts[k]));
+    if (__ballot_sync(gmask, k < nv && dot > radius) & gmask) return;        // separating face (:345)
+    ArgMax best = am_group8(gmask, am_make(dot, k, k < nv));
     if (best.i >= nv) return;                                             // no vertices (:350)
     const int mi = best.i;
     const float max_dot = best.v;
@@ -112,33 +118,36 @@ FX_D void warp_collide_circle_poly(const ShapeDev *s1, Xf t1, const ShapeDev *s2
     m.count = 1;
 }
 
-// axis of least penetration of sa's faces against sb (src/collision.c:669-705): lane = axis*4 + q,
-// q covers vertices q and q+4 of sb.  Returns the face index (or -1) and its signed depth.
-FX_D int warp_separating_axis(const ShapeDev *sa, Xf ta, const ShapeDev *sb, Xf tb, float *depth) {
-    const unsigned int lane = lane_id();
-    const int ax = (int) (lane >> 2), q = (int) (lane & 3u);
-    const int na = sa->nv, nb = sb->nv;
-    const bool ax_ok = ax < na;
-    V2 nrm = v2(0.0f, 0.0f), vert = v2(0.0f, 0.0f);
-    if (ax_ok) {
-        vert = xf_apply(sa->verts[ax], ta);
-        nrm = xf_rotate(sa->normals[ax], ta);
+// farthest vertex of s along v (first maximum wins), src/collision.c:708-724: sequential, one lane
+FX_D int support_index(const ShapeDev *s, Xf t, V2 v) {
+    float max_dot = -FLT_MAX;
+    int max_i = -1;
+    const V2 vl = xf_unrotate(v, t);
+    const int nv = s->nv;
+    for (int i = 0; i < nv; ++i) {
+        float dot = vdot(s->verts[i], vl);
+        if (max_dot < dot) { max_dot = dot; max_i = i; }
     }
-    V2 v = xf_unrotate(vneg(nrm), tb);                 // support direction in sb's frame (:715)
-    ArgMax sup = am_make(0.0f, 0, false);
-    if (q < nb) sup = am_best(sup, am_make(vdot(sb->verts[q], v), q, true));
-    if (q + 4 < nb) sup = am_best(sup, am_make(vdot(sb->verts[q + 4], v), q + 4, true));
-    sup = am_shfl_xor(sup, 1);
-    sup = am_shfl_xor(sup, 2);
+    return max_i;
+}
+
+// axis of least penetration of sa's faces against sb (src/collision.c:669-705): lane k owns axis k.
+// Returns the face index (or -1) and its signed depth.
+FX_D int grp_separating_axis(unsigned int gmask, int k, const ShapeDev *sa, Xf ta, const ShapeDev *sb, Xf tb, float *depth) {
+    const int na = sa->nv;
     float d = -INFINITY;
-    if (ax_ok && sup.i < nb) {
-        V2 sp = xf_apply(sb->verts[sup.i], tb);
-        d = vdot(nrm, vsub(sp, vert));
+    bool ok = false;
+    if (k < na) {
+        V2 vert = xf_apply(sa->verts[k], ta);
+        V2 nrm = xf_rotate(sa->normals[k], ta);
+        int si = support_index(sb, tb, vneg(nrm));
+        if (si >= 0) {
+            V2 sp = xf_apply(sb->verts[si], tb);
+            d = vdot(nrm, vsub(sp, vert));
+            ok = true;
+        }
     }
-    ArgMax best = am_make(d, ax, ax_ok && sup.i < nb);
-    best = am_shfl_xor(best, 4);
-    best = am_shfl_xor(best, 8);
-    best = am_shfl_xor(best, 16);
+    ArgMax best = am_group8(gmask, am_make(d, k, ok));
     if (best.i >= na) { *depth = FLT_MAX; return -1; }
     *depth = best.v;
     return best.i;
@@ -179,31 +188,25 @@ FX_D bool clip_edge(EdgeDev &e, V2 v, float dot) {
     return false;
 }
 
-// polygon vs polygon, src/collision.c:456-558 (warp-cooperative, uniform arguments and result)
-FX_D void warp_collide_polys(const ShapeDev *s1, Xf t1, const ShapeDev *s2, Xf t2, Manifold &m) {
+// polygon vs polygon, src/collision.c:456-558 (group-cooperative, uniform arguments and result)
+FX_D void grp_collide_polys(unsigned int gmask, int k, const ShapeDev *s1, Xf t1, const ShapeDev *s2, Xf t2, Manifold &m) {
     m.count = 0;
     m.has_ids = 1;
     float dep1, dep2;
-    int i1 = warp_separating_axis(s1, t1, s2, t2, &dep1);
+    int i1 = grp_separating_axis(gmask, k, s1, t1, s2, t2, &dep1);
     if (dep1 >= 0.0f) return;
-    int i2 = warp_separating_axis(s2, t2, s1, t1, &dep2);
+    int i2 = grp_separating_axis(gmask, k, s2, t2, s1, t1, &dep2);
     if (dep2 >= 0.0f) return;
 
     V2 dir = (dep1 > dep2) ? xf_rotate(s1->normals[i1], t1) : xf_rotate(s2->normals[i2], t2);
     V2 delta = vsub(t2.p, t1.p);
     if (vdot(delta, dir) < 0.0f) dir = vneg(dir);
 
-    // both support searches at once: lanes 0-7 scan s1 along dir, lanes 8-15 scan s2 along -dir
-    const unsigned int lane = lane_id();
-    const int grp = (int) (lane >> 3), k = (int) (lane & 7u);
-    const ShapeDev *ss = (grp == 0) ? s1 : s2;
-    const Xf ts = (grp == 0) ? t1 : t2;
-    V2 vl = xf_unrotate((grp == 0) ? dir : vneg(dir), ts);
-    ArgMax sup = am_make((grp < 2 && k < ss->nv) ? vdot(ss->verts[k], vl) : 0.0f, k, grp < 2 && k < ss->nv);
-    sup = am_shfl_xor(sup, 1);
-    sup = am_shfl_xor(sup, 2);
-    sup = am_shfl_xor(sup, 4);
-    int si1 = __shfl_sync(0xffffffffu, sup.i, 0), si2 = __shfl_sync(0xffffffffu, sup.i, 8);
+    // the two support searches of frGetContactEdge: lane k scores vertex k, shuffle arg-max
+    V2 vl1 = xf_unrotate(dir, t1), vl2 = xf_unrotate(vneg(dir), t2);
+    ArgMax a1 = am_group8(gmask, am_make(k < s1->nv ? vdot(s1->verts[k], vl1) : 0.0f, k, k < s1->nv));
+    ArgMax a2 = am_group8(gmask, am_make(k < s2->nv ? vdot(s2->verts[k], vl2) : 0.0f, k, k < s2->nv));
+    const int si1 = a1.i, si2 = a2.i;
     if (si1 >= s1->nv || si2 >= s2->nv) return;
 
     EdgeDev e1 = contact_edge_from_support(s1, t1, dir, si1);
@@ -245,14 +248,194 @@ FX_D void warp_collide_polys(const ShapeDev *s1, Xf t1, const ShapeDev *s2, Xf t
     }
 }
 
-// Dispatch for one pair evaluated by a whole warp (uniform arguments), src/collision.c:114-135.
-FX_D void warp_collide(const ShapeDev *s1, Xf t1, const ShapeDev *s2, Xf t2, Manifold &m) {
+// Dispatch for one pair evaluated by a group of 8 lanes (uniform arguments), src/collision.c:114-135.
+FX_D void grp_collide(unsigned int gmask, int k, const ShapeDev *s1, Xf t1, const ShapeDev *s2, Xf t2, Manifold &m) {
     m.count = 0;
     m.has_ids = 0;
-    if (s1 == nullptr || s2 == nullptr) return;
     const int ty1 = s1->type, ty2 = s2->type;
     if (ty1 == FX_SHAPE_CIRCLE && ty2 == FX_SHAPE_CIRCLE) collide_circles(s1->radius, t1, s2->radius, t2, m);
     else if ((ty1 == FX_SHAPE_CIRCLE && ty2 == FX_SHAPE_POLYGON) || (ty1 == FX_SHAPE_POLYGON && ty2 == FX_SHAPE_CIRCLE))
-        warp_collide_circle_poly(s1, t1, s2, t2, m);
-    else if (ty1 == FX_SHAPE_POLYGON && ty2 == FX_SHAPE_POLYGON) warp_collide_polys(s1, t1, s2, t2, m);
+        grp_collide_circle_poly(gmask, k, s1, t1, s2, t2, m);
+    else if (ty1 == FX_SHAPE_POLYGON && ty2 == FX_SHAPE_POLYGON) grp_collide_polys(gmask, k, s1, t1, s2, t2, m);
+}
+
+// ---------------------------------------------------------------------------------------------
+// One lane per pair.  The polygon data of the lane's two shapes sits in shared memory as
+// [shape][component][vertex][lane] (conflict-free: consecutive lanes hit consecutive banks); all 32
+// lanes run the reference's loops verbatim (src/collision.c:305-724), so ties, early-outs and
+// feature ids are the reference's by construction.  The long dependent chains of a pair (sqrt/div in
+// the edge normalisations, clipping) overlap across the 32 pairs of a warp instead of being paid
+// once per pair as in the group-cooperative variant above.  [measured on B200, 65,536-body config 2:
+// warp per pair 248 us, 8 lanes per pair 186 us, lane per pair: see profiles/]
+// ---------------------------------------------------------------------------------------------
+struct LaneShapes {
+    float vx[2][FX_MAX_VERTS][32], vy[2][FX_MAX_VERTS][32];   // vertices
+    float nx[2][FX_MAX_VERTS][32], ny[2][FX_MAX_VERTS][32];   // normals
+};
+
+struct LanePoly {          // what one lane knows about one of its polygons
+    const LaneShapes *sh;
+    int which, lane, nv;
+    FX_D V2 vert(int i) const { return v2(sh->vx[which][i][lane], sh->vy[which][i][lane]); }
+    FX_D V2 normal(int i) const { return v2(sh->nx[which][i][lane], sh->ny[which][i][lane]); }
+};
+
+FX_D void lane_stage_poly(LaneShapes *sh, int which, int lane, const ShapeDev *src, int nv) {
+    const float4 *g = reinterpret_cast<const float4 *>(src);
+    const int q = (nv + 1) >> 1;
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k < q) {
+            float4 v = g[2 + k], n = g[6 + k];
+            sh->vx[which][2 * k][lane] = v.x; sh->vy[which][2 * k][lane] = v.y;
+            sh->vx[which][2 * k + 1][lane] = v.z; sh->vy[which][2 * k + 1][lane] = v.w;
+            sh->nx[which][2 * k][lane] = n.x; sh->ny[which][2 * k][lane] = n.y;
+            sh->nx[which][2 * k + 1][lane] = n.z; sh->ny[which][2 * k + 1][lane] = n.w;
+        }
+}
+
+FX_D int lane_support_index(const LanePoly &s, Xf t, V2 v) {      // src/collision.c:708-724
+    float max_dot = -FLT_MAX;
+    int max_i = -1;
+    const V2 vl = xf_unrotate(v, t);
+    for (int i = 0; i < s.nv; ++i) {
+        float dot = vdot(s.vert(i), vl);
+        if (max_dot < dot) { max_dot = dot; max_i = i; }
+    }
+    return max_i;
+}
+
+FX_D int lane_separating_axis(const LanePoly &sa, Xf ta, const LanePoly &sb, Xf tb, float *depth) {   // :669-705
+    float max_depth = -FLT_MAX;
+    int max_i = -1;
+    for (int i = 0; i < sa.nv; ++i) {
+        V2 vert = xf_apply(sa.vert(i), ta);
+        V2 nrm = xf_rotate(sa.normal(i), ta);
+        int si = lane_support_index(sb, tb, vneg(nrm));
+        if (si < 0) return si;
+        V2 sp = xf_apply(sb.vert(si), tb);
+        float d = vdot(nrm, vsub(sp, vert));
+        if (max_depth < d) { max_depth = d; max_i = i; }
+    }
+    *depth = max_depth;
+    return max_i;
+}
+
+FX_D EdgeDev lane_contact_edge(const LanePoly &s, Xf t, V2 v) {    // :628-666
+    const int si = lane_support_index(s, t, v), nv = s.nv;
+    int prev = (si == 0) ? nv - 1 : si - 1;
+    int next = (si == nv - 1) ? 0 : si + 1;
+    V2 pe = vunit(vsub(s.vert(si), s.vert(prev)));
+    V2 ne = vunit(vsub(s.vert(si), s.vert(next)));
+    V2 vl = xf_unrotate(v, t);
+    V2 sv = xf_apply(s.vert(si), t);
+    EdgeDev e;
+    if (vdot(pe, vl) < vdot(ne, vl)) {
+        e.d0 = xf_apply(s.vert(prev), t); e.d1 = sv; e.d2 = sv; e.i0 = prev; e.i1 = si;
+    } else {
+        e.d0 = sv; e.d1 = xf_apply(s.vert(next), t); e.d2 = sv; e.i0 = si; e.i1 = next;
+    }
+    return e;
+}
+
+FX_D void lane_collide_polys(const LanePoly &s1, Xf t1, const LanePoly &s2, Xf t2, Manifold &m) {   // :456-558
+    m.count = 0;
+    m.has_ids = 1;
+    if (s1.nv <= 0 || s2.nv <= 0) return;
+    float dep1 = FLT_MAX, dep2 = FLT_MAX;
+    int i1 = lane_separating_axis(s1, t1, s2, t2, &dep1);
+    if (dep1 >= 0.0f) return;
+    int i2 = lane_separating_axis(s2, t2, s1, t1, &dep2);
+    if (dep2 >= 0.0f) return;
+
+    V2 dir = (dep1 > dep2) ? xf_rotate(s1.normal(i1), t1) : xf_rotate(s2.normal(i2), t2);
+    V2 delta = vsub(t2.p, t1.p);
+    if (vdot(delta, dir) < 0.0f) dir = vneg(dir);
+
+    EdgeDev e1 = lane_contact_edge(s1, t1, dir);
+    EdgeDev e2 = lane_contact_edge(s2, t2, vneg(dir));
+    EdgeDev ref = e1, inc = e2;
+    float ed1 = vdot(vsub(e1.d1, e1.d0), dir);
+    float ed2 = vdot(vsub(e2.d1, e2.d0), dir);
+    int flipped = 0;
+    if (fabsf(ed1) > fabsf(ed2)) { ref = e2; inc = e1; flipped = 1; }      // :497-502
+
+    V2 rv = vunit(vsub(ref.d1, ref.d0));
+    float rd1 = vdot(ref.d0, rv), rd2 = vdot(ref.d1, rv);
+    if (!clip_edge(inc, rv, rd1)) return;
+    if (!clip_edge(inc, vneg(rv), -rd2)) return;
+
+    V2 rn = vperp_right(rv);
+    float max_depth = vdot(ref.d2, rn);
+    float depth1 = vdot(inc.d0, rn) - max_depth;
+    float depth2 = vdot(inc.d1, rn) - max_depth;
+
+    m.dir = dir;
+    unsigned int mask = ((unsigned int) flipped << 16) | ((unsigned int) ref.i0 << 8);   // :524-528
+    int id0 = (int) (mask | (unsigned int) inc.i0), id1 = (int) (mask | (unsigned int) inc.i1);
+    if (depth1 < 0.0f) {
+        m.id[0] = m.id[1] = id1;
+        m.p[0] = m.p[1] = inc.d1;
+        m.depth[0] = m.depth[1] = depth2;
+        m.count = 1;
+    } else if (depth2 < 0.0f) {
+        m.id[0] = m.id[1] = id0;
+        m.p[0] = m.p[1] = inc.d0;
+        m.depth[0] = m.depth[1] = depth1;
+        m.count = 1;
+    } else {
+        m.id[0] = id0; m.p[0] = inc.d0; m.depth[0] = depth1;
+        m.id[1] = id1; m.p[1] = inc.d1; m.depth[1] = depth2;
+        m.count = 2;
+    }
+}
+
+// circle (radius) vs polygon; `circle_first` tells which body of the pair is the circle  (:305-449)
+FX_D void lane_collide_circle_poly(bool circle_first, float radius, const LanePoly &poly, Xf t1, Xf t2, Manifold &m) {
+    m.count = 0;
+    m.has_ids = 0;
+    const Xf ct = circle_first ? t1 : t2, pt = circle_first ? t2 : t1;
+    const int nv = poly.nv;
+    V2 c = xf_unrotate(vsub(ct.p, pt.p), pt);
+    float max_dot = -FLT_MAX;
+    int mi = -1;
+    for (int i = 0; i < nv; ++i) {                      // :340-348
+        float dot = vdot(poly.normal(i), vsub(c, poly.vert(i)));
+        if (dot > radius) return;
+        if (max_dot < dot) { max_dot = dot; mi = i; }
+    }
+    if (mi < 0) return;
+    V2 delta = vsub(t2.p, t1.p);
+    if (max_dot < 0.0f) {
+        m.dir = vneg(xf_rotate(poly.normal(mi), pt));
+        if (vdot(delta, m.dir) < 0.0f) m.dir = vneg(m.dir);
+        m.p[0] = vadd(ct.p, vscale(m.dir, radius));
+        m.depth[0] = radius - max_dot;
+    } else {
+        V2 p1 = (mi > 0) ? poly.vert(mi - 1) : poly.vert(nv - 1);
+        V2 p2 = poly.vert(mi);
+        V2 edge = vsub(p2, p1);
+        V2 p1c = vsub(c, p1), p2c = vsub(c, p2);
+        float d1 = vdot(p1c, edge), d2 = vdot(p2c, vneg(edge));
+        if (d1 < 0.0f || d2 < 0.0f) {
+            V2 dv = (d1 < 0.0f) ? p1c : p2c;
+            float m2 = vlen2(dv);
+            if (radius * radius < m2) return;
+            float mag = sqrtf(m2);
+            if (mag <= 0.0f) mag = FLT_EPSILON;
+            m.dir = vscale(xf_rotate(vneg(dv), pt), 1.0f / mag);
+            if (vdot(delta, m.dir) < 0.0f) m.dir = vneg(m.dir);
+            m.p[0] = xf_apply(vscale(m.dir, radius), ct);
+            m.depth[0] = radius - mag;
+        } else {
+            m.dir = vneg(xf_rotate(poly.normal(mi), pt));
+            if (vdot(delta, m.dir) < 0.0f) m.dir = vneg(m.dir);
+            m.p[0] = vadd(ct.p, vscale(m.dir, radius));
+            m.depth[0] = radius - max_dot;
+        }
+    }
+    m.p[1] = m.p[0];
+    m.depth[1] = m.depth[0];
+    m.id[0] = m.id[1] = 0;
+    m.count = 1;
 }

@@ -68,23 +68,47 @@ FX_D unsigned int claim_tile(unsigned int *ticket) {
 }
 
 // Exclusive prefix of `tile_total` over all tiles with a smaller index.  Called by the whole block
-// with a block-uniform tile_total; one thread walks back over the predecessors.
+// with a block-uniform tile_total.  The WHOLE BLOCK looks back, blockDim.x predecessors per hop: it
+// adds up tile aggregates until it meets a tile that already knows its inclusive prefix.  With
+// hundreds of tiles in flight the prefix frontier advances one window per L2 round trip, so the
+// window width sets the speed of every ordered sweep ([measured] narrow phase, 4,216 tiles of the
+// 65k-body config: 1 thread 186 us, one warp 177 us; see DESIGN.md for the block-wide figure).
 FX_D unsigned int tile_exclusive_prefix(unsigned long long *status, unsigned int tile,
                                         unsigned int tile_total) {
+    __shared__ unsigned long long s_part[32];
+    __shared__ int s_near[32];
     __shared__ unsigned int s_prefix;
-    if (threadIdx.x == 0) {
-        unsigned long long excl = 0ull;
-        if (tile > 0) {
-            st_status(&status[tile], FX_TILE_AGG | (unsigned long long) tile_total);
-            int t = (int) tile - 1;
-            for (;;) {
-                unsigned long long s;
-                do { s = ld_status(&status[t]); } while ((s >> 62) == 0ull);
-                excl += (s & FX_TILE_VAL);
-                if ((s >> 62) == 2ull) break;
-                --t;
+    const unsigned int tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, nwarps = (blockDim.x + 31u) >> 5;
+    unsigned long long excl = 0ull;
+    if (tile > 0) {
+        if (tid == 0) st_status(&status[tile], FX_TILE_AGG | (unsigned long long) tile_total);
+        int base = (int) tile - 1;                      // nearest predecessor of this window
+        for (;;) {
+            const int idx = base - (int) tid;
+            unsigned long long s = FX_TILE_PFX;         // before the first tile: prefix 0
+            if (idx >= 0) {
+                do { s = ld_status(&status[idx]); } while ((s >> 62) == 0ull);
             }
+            // nearest predecessor (smallest tid) that already holds an inclusive prefix
+            int near = ((s >> 62) == 2ull) ? (int) tid : 0x7fffffff;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) near = min(near, __shfl_xor_sync(0xffffffffu, near, d));
+            if (lane == 0) s_near[warp] = near;
+            __syncthreads();
+            int stop = 0x7fffffff;
+            for (unsigned int k = 0; k < nwarps; ++k) stop = min(stop, s_near[k]);
+            unsigned long long v = ((int) tid <= stop) ? (s & FX_TILE_VAL) : 0ull;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+            if (lane == 0) s_part[warp] = v;
+            __syncthreads();
+            for (unsigned int k = 0; k < nwarps; ++k) excl += s_part[k];
+            __syncthreads();
+            if (stop != 0x7fffffff) break;
+            base -= (int) blockDim.x;
         }
+    }
+    if (tid == 0) {
         st_status(&status[tile], FX_TILE_PFX | (excl + (unsigned long long) tile_total));
         s_prefix = (unsigned int) excl;
     }

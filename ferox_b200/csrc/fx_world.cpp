@@ -560,6 +560,10 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.dt = dt;
     d.inv_dt = 1.0f / dt;                                       // src/world.c:242
     d.solver_mode = w->solver_mode;
+    {
+        static const int narrow = [] { const char *e = std::getenv("FEROX_NARROWPHASE"); return (e && std::strcmp(e, "group8") == 0) ? 1 : 0; }();
+        d.narrow_mode = narrow;
+    }
     d.idx_of_uid = w->d_idx_of_uid;
     d.shapes = w->d_shapes;
 }
@@ -1089,6 +1093,7 @@ static Scratch *scratch() {
     cudaMallocHost((void **) &s.hcol, sizeof(CollisionPod)); cudaMallocHost((void **) &s.hout, sizeof(Manifold));
     d.shapes = s.d_shapes;
     d.n = 2;
+    { const char *e = std::getenv("FEROX_NARROWPHASE"); d.narrow_mode = (e && std::strcmp(e, "group8") == 0) ? 1 : 0; }
     s.cx.stream = s.stream;
     s.cx.max_blocks = 148 * 8;
     s.ready = fx_cuda_ok(cudaGetLastError(), "scratch init");
