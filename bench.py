@@ -269,12 +269,9 @@ def run_b200(args):
     # ---- max over ranks ----
     if dist is not None:
         import torch
-        t = torch.tensor([elapsed_ms, warm_ms, e2e_s, stage_ms[3]], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms, warm_ms, e2e_s, solve_ms_total = [float(x) for x in t.tolist()]
-        cnt = torch.tensor([n], dtype=torch.float64, device="cuda")
-        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
-        total_bodies = int(cnt.item())
+        from ferox_b200 import sharding
+        elapsed_ms, total_bodies, (warm_ms, e2e_s, solve_ms_total) = sharding.reduce_report(
+            dist, torch.device("cuda", local_rank), elapsed_ms, n, extra_max=(warm_ms, e2e_s, stage_ms[3]))
     else:
         solve_ms_total = float(stage_ms[3])
         total_bodies = n

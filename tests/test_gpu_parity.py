@@ -80,6 +80,18 @@ def test_reference_ut_circle_vs_polygon(gpu):
     assert abs(col.contacts[0].depth - (1.0 - float(np.sqrt(np.float32(0.01) ** 2 * 2)))) <= EPS
 
 
+def test_reference_test_binary_relinked(gpu):
+    """The reference's own unit-test PROGRAM (tests/src/*.c compiled against the reference's ferox.h)
+    linked against libferox.so instead of the reference library (oracle/Makefile `relink`)."""
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.dirname(__file__)), "oracle", "_ref", "ferox_tests_relinked.out")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ferox_tests_relinked.out not built")
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "Pass: 6, fail: 0" in out.stdout, out.stdout[-600:]
+
+
 def test_known_answer_two_boxes(gpu):
     """two 2x1 boxes at (0,0) and (0.5,0.9)."""
     L = gpu
