@@ -280,6 +280,20 @@ struct LanePoly {          // what one lane knows about one of its polygons
     FX_D V2 normal(int i) const { return v2(sh->nx[which][i][lane], sh->ny[which][i][lane]); }
 };
 
+// polygon read straight from the shape table (read-only for the whole kernel: L1-cacheable loads)
+struct GlobalPoly {
+    const ShapeDev *s;
+    int nv;
+    FX_D V2 vert(int i) const {
+        float2 v = __ldg(reinterpret_cast<const float2 *>(&s->verts[i]));
+        return v2(v.x, v.y);
+    }
+    FX_D V2 normal(int i) const {
+        float2 v = __ldg(reinterpret_cast<const float2 *>(&s->normals[i]));
+        return v2(v.x, v.y);
+    }
+};
+
 FX_D void lane_stage_poly(LaneShapes *sh, int which, int lane, const ShapeDev *src, int nv) {
     const float4 *g = reinterpret_cast<const float4 *>(src);
     const int q = (nv + 1) >> 1;
@@ -294,7 +308,8 @@ FX_D void lane_stage_poly(LaneShapes *sh, int which, int lane, const ShapeDev *s
         }
 }
 
-FX_D int lane_support_index(const LanePoly &s, Xf t, V2 v) {      // src/collision.c:708-724
+template <class P>
+FX_D int lane_support_index(const P &s, Xf t, V2 v) {      // src/collision.c:708-724
     float max_dot = -FLT_MAX;
     int max_i = -1;
     const V2 vl = xf_unrotate(v, t);
@@ -305,7 +320,8 @@ FX_D int lane_support_index(const LanePoly &s, Xf t, V2 v) {      // src/collisi
     return max_i;
 }
 
-FX_D int lane_separating_axis(const LanePoly &sa, Xf ta, const LanePoly &sb, Xf tb, float *depth) {   // :669-705
+template <class P>
+FX_D int lane_separating_axis(const P &sa, Xf ta, const P &sb, Xf tb, float *depth) {   // :669-705
     float max_depth = -FLT_MAX;
     int max_i = -1;
     for (int i = 0; i < sa.nv; ++i) {
@@ -321,7 +337,8 @@ FX_D int lane_separating_axis(const LanePoly &sa, Xf ta, const LanePoly &sb, Xf 
     return max_i;
 }
 
-FX_D EdgeDev lane_contact_edge(const LanePoly &s, Xf t, V2 v) {    // :628-666
+template <class P>
+FX_D EdgeDev lane_contact_edge(const P &s, Xf t, V2 v) {    // :628-666
     const int si = lane_support_index(s, t, v), nv = s.nv;
     int prev = (si == 0) ? nv - 1 : si - 1;
     int next = (si == nv - 1) ? 0 : si + 1;
@@ -338,7 +355,8 @@ FX_D EdgeDev lane_contact_edge(const LanePoly &s, Xf t, V2 v) {    // :628-666
     return e;
 }
 
-FX_D void lane_collide_polys(const LanePoly &s1, Xf t1, const LanePoly &s2, Xf t2, Manifold &m) {   // :456-558
+template <class P>
+FX_D void lane_collide_polys(const P &s1, Xf t1, const P &s2, Xf t2, Manifold &m) {   // :456-558
     m.count = 0;
     m.has_ids = 1;
     if (s1.nv <= 0 || s2.nv <= 0) return;
@@ -391,7 +409,8 @@ FX_D void lane_collide_polys(const LanePoly &s1, Xf t1, const LanePoly &s2, Xf t
 }
 
 // circle (radius) vs polygon; `circle_first` tells which body of the pair is the circle  (:305-449)
-FX_D void lane_collide_circle_poly(bool circle_first, float radius, const LanePoly &poly, Xf t1, Xf t2, Manifold &m) {
+template <class P>
+FX_D void lane_collide_circle_poly(bool circle_first, float radius, const P &poly, Xf t1, Xf t2, Manifold &m) {
     m.count = 0;
     m.has_ids = 0;
     const Xf ct = circle_first ? t1 : t2, pt = circle_first ? t2 : t1;

@@ -561,7 +561,7 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.inv_dt = 1.0f / dt;                                       // src/world.c:242
     d.solver_mode = w->solver_mode;
     {
-        static const int narrow = [] { const char *e = std::getenv("FEROX_NARROWPHASE"); return (e && std::strcmp(e, "group8") == 0) ? 1 : 0; }();
+        static const int narrow = [] { const char *e = std::getenv("FEROX_NARROWPHASE"); return !e ? 0 : (std::strcmp(e, "group8") == 0 ? 1 : (std::strcmp(e, "lane") == 0 ? 2 : 0)); }();
         d.narrow_mode = narrow;
     }
     d.idx_of_uid = w->d_idx_of_uid;
