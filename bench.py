@@ -48,11 +48,41 @@ def parse_args():
     ap.add_argument("--bodies", type=int, default=65536)
     ap.add_argument("--settle", type=int, default=600)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
+                    help="config2 (default, the headline): one 65,536-body mixed pile per GPU; config4: 4,096 "
+                         "independent 256-body worlds batched into one launch set and sharded over the GPUs")
+    ap.add_argument("--worlds", type=int, default=4096)
     return ap.parse_args()
 
 
 def workload_name(n):
     return "config2: %d mixed circles + convex polygons (3-8 verts) pile + 3 static walls, cell 2.0, dt 1/60" % n
+
+
+def build_config4_batch(L, n_worlds, rank, world_size):
+    """BASELINE config 4: the worlds this rank owns (round-robin), batched into ONE pipeline."""
+    from ferox_b200 import capi, scenes, sharding
+    mine = sharding.owned_worlds(n_worlds, rank, world_size)
+    specs = [scenes.small_world(sharding.world_seed(0, w)) for w in mine]
+    shape_specs = specs[0].shapes                      # every small world uses the same 5 shapes
+    shapes = (C.c_void_p * len(shape_specs))(*[scenes.make_shape(L, s) for s in shape_specs])
+    total = sum(s.n for s in specs)
+    world = L.frxCreateWorldBatch(capi.Vector2(*specs[0].gravity), specs[0].cell, len(specs))
+    L.frxSetWorldCapacity(world, total + 16)
+    cat = lambda f, dt: np.ascontiguousarray(np.concatenate([getattr(s, f) for s in specs]).astype(dt))
+    group = np.ascontiguousarray(np.concatenate([np.full(s.n, k, np.int32) for k, s in enumerate(specs)]))
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    pos, ang, vel, om = cat("pos", np.float32), cat("angle", np.float32), cat("vel", np.float32), cat("omega", np.float32)
+    got = L.frxCreateBodiesEx(world, total, cat("body_type", np.int32), cat("body_shape", np.int32), shapes,
+                              pos.reshape(-1), ptr(ang), ptr(vel), ptr(om), ptr(group), None)
+    assert got == total, (got, total)
+
+    class Batch:
+        pass
+    b = Batch()
+    b.world, b.lib, b.n_worlds = world, L, len(specs)
+    b.release = lambda: L.frReleaseWorld(world)
+    return b
 
 
 # ------------------------------------------------------------------------------------------------
@@ -199,12 +229,17 @@ def run_b200(args):
     if L.frxSetDevice(local_rank) != 0:
         raise SystemExit("no CUDA device %d: the ferox world step has no CPU fallback" % local_rank)
 
-    spec = scenes.mixed_pile(args.bodies, seed=1234 + rank)
-    sc = scenes.Scene(L, spec, prime=False)
     dt = scenes.DT
-    L.frStepWorld(sc.world, dt)                      # priming step: queued bodies enter the world
-    n = L.frGetBodyCountInWorld(sc.world)
-    assert n == spec.n, (n, spec.n)
+    if args.workload == "config4":
+        sc = build_config4_batch(L, args.worlds, rank, world_size)
+        L.frStepWorld(sc.world, dt)
+        n = L.frGetBodyCountInWorld(sc.world)
+    else:
+        spec = scenes.mixed_pile(args.bodies, seed=1234 + rank)
+        sc = scenes.Scene(L, spec, prime=False)
+        L.frStepWorld(sc.world, dt)                  # priming step: queued bodies enter the world
+        n = L.frGetBodyCountInWorld(sc.world)
+        assert n == spec.n, (n, spec.n)
     L.frxStepWorldN(sc.world, dt, args.settle)       # settle the pile (untimed)
     L.frxSynchronizeWorld(sc.world)
     fb.check_error(L)
@@ -290,10 +325,16 @@ def run_b200(args):
         step_bytes = (n * (160 + 2 * 24) + 104 * ctr["cellEntries"] + ctr["candidates"] * (64 + 92) + 1060 * M + 376 * Q)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": warm,
-            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if args.workload == "config4" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.bodies), "bodies_per_gpu": n, "settle_steps": args.settle,
-                       "solver": "graph-coloured PGS, 10 iterations", "parallelism": "independent worlds, 1 per GPU",
+            "config": {"workload": workload_name(args.bodies) if args.workload == "config2" else
+                       "config4: %d independent worlds x 256 bodies (252 dynamic mixed + floor + 2 walls + kinematic paddle), "
+                       "batched into one launch set per GPU" % args.worlds,
+                       "bodies_per_gpu": n, "settle_steps": args.settle,
+                       "solver": "graph-coloured PGS, 10 iterations",
+                       "parallelism": "independent worlds, 1 per GPU" if args.workload == "config2" else
+                       "worlds sharded round-robin over the GPUs, no communication",
                        "l2": "flushed between timed steps (256 MiB memset on the step's stream, outside the event bracket)",
                        "counters": ctr},
             "value_warm_l2": total_bodies * args.steps / (warm_ms * 1e-3),
@@ -308,7 +349,7 @@ def run_b200(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and args.workload == "config2":
             line["cpu_baseline"] = cpu_baseline(sc, n)
         print(json.dumps(line))
         sys.stdout.flush()

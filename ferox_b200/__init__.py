@@ -43,6 +43,9 @@ EXT_PROTOTYPES = {
     "frxGetLastErrorString": (C.c_char_p, []),
     "frxSetWorldCapacity": (C.c_bool, [P, I]),
     "frxGetWorldCapacity": (I, [P]),
+    "frxCreateWorldBatch": (P, [capi.Vector2, F, I]),
+    "frxAddBodyToBatch": (C.c_bool, [P, I, P]),
+    "frxGetBatchWorldCount": (I, [P]),
     "frxSetWorldSolverMode": (None, [P, I]),
     "frxGetWorldSolverMode": (I, [P]),
     "frxSetWorldTimestamp": (None, [P, F]),
@@ -54,6 +57,7 @@ EXT_PROTOTYPES = {
     "frxApplyForces": (I, [P, P, P, I]),
     "frxSetBodyVelocities": (I, [P, P, P, I]),
     "frxCreateBodies": (I, [P, I, i32p, i32p, P, f32p, P, P]),
+    "frxCreateBodiesEx": (I, [P, I, i32p, i32p, P, f32p, P, P, P, P, P]),
     "frxGetCandidatePairs": (I, [P, P, I]),
     "frxGetManifolds": (I, [P, P, I]),
     "frxComputeCollisions": (I, [P, i32p, I, P, P]),

@@ -149,7 +149,9 @@ __global__ void k_plan(DevWorld w) {
         gh = (unsigned long long) ((long long) c->cell_max_y - c->cell_min_y + 1);
     }
     unsigned long long cells = gw * gh;
-    if (gw > 0xffffffffull || gh > 0xffffffffull || cells > 0x100000000ull) {
+    const unsigned long long groups = (w.group != nullptr && w.n_groups > 1) ? (unsigned long long) w.n_groups : 1ull;
+    // batched worlds: the key is group * (W*H) + cell, so bodies of different sub-worlds never share a run
+    if (gw > 0xffffffffull || gh > 0xffffffffull || cells > 0x100000000ull || cells * groups > 0x100000000ull) {
         // the dense key does not fit 32 bits: refuse loudly (host reports it), emit nothing
         c->overflow |= 16u;
         c->n_entries = 0;
@@ -159,7 +161,7 @@ __global__ void k_plan(DevWorld w) {
     c->grid_w = (unsigned int) gw;
     c->grid_h = (unsigned int) gh;
     unsigned int bits = 1;
-    while (bits < 32 && (1ull << bits) < cells) ++bits;
+    while (bits < 32 && (1ull << bits) < cells * groups) ++bits;
     c->key_bits = bits;
     c->sort_passes = (bits + 7) / 8;
 }
@@ -169,6 +171,7 @@ __device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, 
                                            unsigned int gw) {
     if (pos >= w.cap_entries) return;
     unsigned int key = (unsigned int) (y - miny) * gw + (unsigned int) (x - minx);
+    if (w.group != nullptr) key += (unsigned int) w.group[body] * (gw * w.ctr->grid_h);
     unsigned int v = body | massbit | (x == r.x0 ? ENT_X0 : 0u) | (y == r.y0 ? ENT_Y0 : 0u);
     w.keys[0][pos] = key;
     w.vals[0][pos] = v;

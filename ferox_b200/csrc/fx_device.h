@@ -114,6 +114,8 @@ struct DevWorld {
     float *angle;
     int2 *shape;
     unsigned int *uid;
+    const int *group;    // batched worlds: sub-world index per body (nullptr: a single world)
+    int n_groups;
     int *idx_of_uid;     // uid -> world index, -1 when the body left the world
     const ShapeDev *shapes;
     // broadphase scratch

@@ -43,6 +43,7 @@ struct frBody_ {
     frWorld *world;      // non-null while the body is a member of world->bodies
     int index;           // world index while in a world
     uint32_t uid;        // stable id while in a world (contact-cache key)
+    int group;           // sub-world index inside a batch (0 in a plain world)
     BodyRow loc;         // dynamic state while outside a world
 };
 
@@ -64,6 +65,7 @@ struct HostMirror {     // pinned host arrays, capacity `cap`
     float *angle = nullptr;
     int2 *shape = nullptr;
     unsigned int *uid = nullptr;
+    int *group = nullptr;
 };
 
 struct frWorld_ {
@@ -80,6 +82,8 @@ struct frWorld_ {
     float accumulator = 0.f, timestamp = 0.f;
     frCollisionHandler handler{ nullptr, nullptr };
     int solver_mode = FRX_SOLVER_COLORED;
+    int n_groups = 1;                // > 1: a batch of independent sub-worlds sharing this pipeline
+    int *d_group = nullptr;
 
     HostMirror h;
     unsigned dirty = 0;

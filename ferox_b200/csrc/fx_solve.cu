@@ -290,12 +290,9 @@ __device__ void so_put(const SerialOrder &o, unsigned long long key) {   // hmpu
     o.t_key[s] = key;
     o.t_val[s] = pos;
 }
-__device__ void so_del(const SerialOrder &o, unsigned long long key) {   // hmdel: swap-delete
-    int s = so_find(o, key);
-    if (s < 0) return;
-    unsigned int old_index = o.t_val[s], final_index = *o.r_len - 1u;
+__device__ void so_erase_slot(const SerialOrder &o, int s) {   // backward-shift deletion of an index slot
     unsigned int mask = o.t_cap - 1u, hole = (unsigned int) s, j = (unsigned int) s;
-    for (;;) {   // backward-shift deletion
+    for (;;) {
         j = (j + 1u) & mask;
         unsigned long long kj = o.t_key[j];
         if (kj == 0xffffffffffffffffull) break;
@@ -307,12 +304,36 @@ __device__ void so_del(const SerialOrder &o, unsigned long long key) {   // hmde
         }
     }
     o.t_key[hole] = 0xffffffffffffffffull;
+}
+__device__ __forceinline__ int key_group(const DevWorld &w, unsigned long long key) {
+    if (w.group == nullptr) return 0;
+    int i = w.idx_of_uid[(unsigned int) (key >> 32)];
+    return i >= 0 ? w.group[i] : -1;
+}
+// hmdel: swap-delete.  In a batch every sub-world must keep the array discipline it would have on
+// its own, so the hole is filled with the last entry OF THE SAME SUB-WORLD and the slot that entry
+// leaves is closed by a stable shift (other sub-worlds keep their relative order).
+__device__ void so_del(const DevWorld &w, const SerialOrder &o, unsigned long long key) {
+    int s = so_find(o, key);
+    if (s < 0) return;
+    const unsigned int old_index = o.t_val[s], len = *o.r_len;
+    so_erase_slot(o, s);
+    unsigned int final_index = len - 1u;
+    if (w.group != nullptr) {
+        const int g = key_group(w, key);
+        while (final_index > old_index && key_group(w, o.r_key[final_index]) != g) --final_index;
+    }
     if (old_index != final_index) {
         unsigned long long moved = o.r_key[final_index];
         o.r_key[old_index] = moved;
         o.t_val[so_find(o, moved)] = old_index;
     }
-    *o.r_len = final_index;
+    for (unsigned int p = final_index; p + 1u < len; ++p) {      // no-op in a plain world
+        unsigned long long k = o.r_key[p + 1u];
+        o.r_key[p] = k;
+        o.t_val[so_find(o, k)] = p;
+    }
+    *o.r_len = len - 1u;
 }
 
 __device__ __forceinline__ int cache_lookup(const DevWorld &w, unsigned long long key) {
@@ -336,7 +357,7 @@ __global__ void k_serial_order(DevWorld w, SerialOrder o) {
         int2 pr = w.cand[c];
         unsigned long long key = ((unsigned long long) w.uid[pr.x] << 32) | (unsigned long long) w.uid[pr.y];
         if (w.cand_hit[c]) so_put(o, key);
-        else so_del(o, key);
+        else so_del(w, o, key);
     }
     // entries that the new dense array no longer holds (timestamp rule, departed bodies): the
     // reference walks j = 0 .. entryCount-1 of the pre-loop length while hmdel shrinks the array, so
@@ -345,12 +366,12 @@ __global__ void k_serial_order(DevWorld w, SerialOrder o) {
     for (unsigned int j = 0; j < entry_count; ++j) {
         if (j >= *o.r_len) break;   // (the reference reads stale tail bytes here; not replayed)
         unsigned long long key = o.r_key[j];
-        if (cache_lookup(w, key) < 0) so_del(o, key);
+        if (cache_lookup(w, key) < 0) so_del(w, o, key);
     }
     // anything still missing (skipped by the quirk above but gone from the dense array) must go,
     // otherwise the solver would dereference a missing entry
     for (unsigned int j = 0; j < *o.r_len;) {
-        if (cache_lookup(w, o.r_key[j]) < 0) so_del(o, o.r_key[j]);
+        if (cache_lookup(w, o.r_key[j]) < 0) so_del(w, o, o.r_key[j]);
         else ++j;
     }
 }

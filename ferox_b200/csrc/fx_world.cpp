@@ -171,6 +171,8 @@ static void world_free_device(frWorld *w) {
     if (h.angle) cudaFreeHost(h.angle);
     if (h.shape) cudaFreeHost(h.shape);
     if (h.uid) cudaFreeHost(h.uid);
+    if (h.group) cudaFreeHost(h.group);
+    cudaFree(w->d_group);
     if (w->snapshot_ready) cudaEventDestroy(w->snapshot_ready);
     for (cudaEvent_t e : w->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : w->user_events) if (e) cudaEventDestroy(e);
@@ -208,6 +210,20 @@ extern "C" bool frAddBodyToWorld(frWorld *w, frBody *b) {
     if (!w || !b || (int) w->bodies.size() >= w->capacity) return false;
     return ring_push(w, WorldOp{ FX_OP_ADD, b });
 }
+// ---- batched independent worlds (BASELINE config 4) ----
+extern "C" frWorld *frxCreateWorldBatch(frVector2 gravity, float cellSize, int nWorlds) {
+    if (nWorlds <= 0) return nullptr;
+    frWorld *w = frCreateWorld(gravity, cellSize);
+    if (w) w->n_groups = nWorlds;
+    return w;
+}
+extern "C" int frxGetBatchWorldCount(const frWorld *w) { return w ? w->n_groups : 0; }
+extern "C" bool frxAddBodyToBatch(frWorld *w, int worldIndex, frBody *b) {
+    if (!w || !b || worldIndex < 0 || worldIndex >= w->n_groups) return false;
+    if (b->world == nullptr) b->group = worldIndex;
+    return frAddBodyToWorld(w, b);
+}
+
 extern "C" bool frRemoveBodyFromWorld(frWorld *w, frBody *b) {
     if (!w || !b) return false;
     return ring_push(w, WorldOp{ FX_OP_REMOVE, b });
@@ -253,13 +269,13 @@ static bool ensure_body_capacity(frWorld *w, int need) {
     HostMirror &h = w->h;
     bool ok = pin_realloc(h.posrot, o, n) && pin_realloc(h.vel, o, n) && pin_realloc(h.mprop, o, n) &&
               pin_realloc(h.force, o, n) && pin_realloc(h.aabb, o, n) && pin_realloc(h.angle, o, n) &&
-              pin_realloc(h.shape, o, n) && pin_realloc(h.uid, o, n);
+              pin_realloc(h.shape, o, n) && pin_realloc(h.uid, o, n) && pin_realloc(h.group, o, n);
     h.cap = cap;
     DevWorld &d = w->dw;
     cudaStream_t s = w->stream;
     ok = ok && dev_realloc(d.posrot, o, n, s, true) && dev_realloc(d.vel, o, n, s, true) && dev_realloc(d.mprop, o, n, s, true) &&
          dev_realloc(d.force, o, n, s, true) && dev_realloc(d.aabb, o, n, s, true) && dev_realloc(d.angle, o, n, s, true) &&
-         dev_realloc(d.shape, o, n, s, true) && dev_realloc(d.uid, o, n, s, true) &&
+         dev_realloc(d.shape, o, n, s, true) && dev_realloc(d.uid, o, n, s, true) && dev_realloc(w->d_group, o, n, s, true) &&
          dev_realloc(d.cell_cnt, 0, n, s, false) && dev_realloc(d.cell_off, 0, n, s, false) &&
          dev_realloc(d.large_list, 0, n, s, false) && dev_realloc(d.body_mask, 0, n, s, false) && dev_realloc(d.body_dup, 0, n, s, false) &&
          dev_realloc(d.winner, 0, n, s, false);
@@ -301,7 +317,10 @@ static void world_push(frWorld *w) {
         if (d & FX_DIRTY_FORCE) cudaMemcpyAsync(w->dw.force, w->h.force, n * sizeof(float4), cudaMemcpyHostToDevice, s);
         if (d & FX_DIRTY_AABB) cudaMemcpyAsync(w->dw.aabb, w->h.aabb, n * sizeof(float4), cudaMemcpyHostToDevice, s);
         if (d & FX_DIRTY_SHAPE) cudaMemcpyAsync(w->dw.shape, w->h.shape, n * sizeof(int2), cudaMemcpyHostToDevice, s);
-        if (d & FX_DIRTY_UID) cudaMemcpyAsync(w->dw.uid, w->h.uid, n * sizeof(unsigned int), cudaMemcpyHostToDevice, s);
+        if (d & FX_DIRTY_UID) {
+            cudaMemcpyAsync(w->dw.uid, w->h.uid, n * sizeof(unsigned int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(w->d_group, w->h.group, n * sizeof(int), cudaMemcpyHostToDevice, s);
+        }
     }
     w->dirty = 0;
     if (w->uid_dirty) {
@@ -391,6 +410,7 @@ static void attach_body(frWorld *w, frBody *b) {
     h.force[i] = b->loc.force; h.aabb[i] = b->loc.aabb;
     h.shape[i] = make_int2(shape_slot(w, b->shape), b->shape ? (int) b->shape->type : 0);
     h.uid[i] = uid;
+    h.group[i] = b->group;
     b->world = w; b->index = i; b->uid = uid;
     w->bodies.push_back(b);
     w->dirty = FX_DIRTY_ALL;
@@ -409,6 +429,7 @@ static void detach_body(frWorld *w, frBody *b) {
         frBody *m = w->bodies[last];
         h.posrot[i] = h.posrot[last]; h.angle[i] = h.angle[last]; h.vel[i] = h.vel[last]; h.mprop[i] = h.mprop[last];
         h.force[i] = h.force[last]; h.aabb[i] = h.aabb[last]; h.shape[i] = h.shape[last]; h.uid[i] = h.uid[last];
+        h.group[i] = h.group[last];
         w->bodies[i] = m;
         m->index = i;
         w->uid_index[m->uid] = i;
@@ -566,6 +587,8 @@ static void fill_dev_params(frWorld *w, float dt) {
     }
     d.idx_of_uid = w->d_idx_of_uid;
     d.shapes = w->d_shapes;
+    d.group = (w->n_groups > 1) ? w->d_group : nullptr;
+    d.n_groups = w->n_groups;
 }
 
 static void read_snapshot(frWorld *w, bool wait) {
@@ -1041,6 +1064,29 @@ extern "C" int frxCreateBodies(frWorld *w, int n, const int *bodyType, const int
         if (angle && angle[i] != 0.0f) frSetBodyAngle(b, angle[i]);
         if (outBodies) outBodies[i] = b;
         if (frAddBodyToWorld(w, b)) ++accepted;
+    }
+    return accepted;
+}
+
+extern "C" int frxCreateBodiesEx(frWorld *w, int n, const int *bodyType, const int *shapeIndex, frShape *const *shapes,
+                                 const float *position, const float *angle, const float *velocity,
+                                 const float *angularVelocity, const int *worldIndex, frBody **outBodies) {
+    if (!w || n <= 0 || !bodyType || !position) return 0;
+    int accepted = 0;
+    for (int i = 0; i < n; ++i) {
+        frVector2 p = { position[2 * i], position[2 * i + 1] };
+        frShape *s = (shapes && shapeIndex && shapeIndex[i] >= 0) ? shapes[shapeIndex[i]] : nullptr;
+        frBody *b = frCreateBodyFromShape((frBodyType) bodyType[i], p, s);
+        if (!b) { if (outBodies) outBodies[i] = nullptr; continue; }
+        if (angle && angle[i] != 0.0f) frSetBodyAngle(b, angle[i]);
+        if (velocity && (velocity[2 * i] != 0.0f || velocity[2 * i + 1] != 0.0f)) {
+            frVector2 v = { velocity[2 * i], velocity[2 * i + 1] };
+            frSetBodyVelocity(b, v);
+        }
+        if (angularVelocity && angularVelocity[i] != 0.0f) frSetBodyAngularVelocity(b, angularVelocity[i]);
+        if (outBodies) outBodies[i] = b;
+        bool ok = worldIndex ? frxAddBodyToBatch(w, worldIndex[i], b) : frAddBodyToWorld(w, b);
+        if (ok) ++accepted;
     }
     return accepted;
 }

@@ -215,7 +215,10 @@ def small_world(world_index=0, n_dynamic=252):
     shapes = [0, 1, 1, 2]
     pos = [(20.0, 1.0), (-1.0, -28.0), (41.0, -28.0), (20.0, -6.0)]
     angle = [0.0] * 4
-    vel = [(0.0, 0.0)] * 3 + [(2.0, 0.0)]
+    # the paddle is a kinematic stirrer: it spins in place (a translating paddle eventually crushes
+    # bodies against a wall and the squeezed bodies are shot out of the world)
+    vel = [(0.0, 0.0)] * 4
+    omega = [0.0, 0.0, 0.0, 1.0]
     per_row = 24
     for k in range(n_dynamic):
         row, col = divmod(k, per_row)
@@ -227,7 +230,8 @@ def small_world(world_index=0, n_dynamic=252):
         pos.append((x, y))
         angle.append(rng.uniform() * 2.0 * math.pi if box else 0.0)
         vel.append((0.0, 0.0))
-    return _finish(spec, types, shapes, pos, angle, vel)
+        omega.append(0.0)
+    return _finish(spec, types, shapes, pos, angle, vel, omega)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -383,3 +387,37 @@ class ManifoldRecorder:
     def remove(self):
         self.scene.lib.frSetWorldCollisionHandler(
             self.scene.world, capi.CollisionHandler(capi.CollisionEventFunc(), capi.CollisionEventFunc()))
+
+
+class BatchScene:
+    """Several SceneSpecs realised as ONE batch of independent sub-worlds (product only,
+    frxCreateWorldBatch): a single device pipeline steps all of them with one launch set."""
+
+    def __init__(self, lib, specs):
+        self.lib, self.specs = lib, specs
+        total = sum(s.n for s in specs)
+        self.world = lib.frxCreateWorldBatch(capi.Vector2(*specs[0].gravity), specs[0].cell, len(specs))
+        lib.frxSetWorldCapacity(self.world, total + 16)
+        self.shapes, self.bodies, self.ranges = [], [], []
+        for k, spec in enumerate(specs):
+            shapes = [make_shape(lib, s) for s in spec.shapes]
+            self.shapes += shapes
+            start = len(self.bodies)
+            for i in range(spec.n):
+                b = lib.frCreateBodyFromShape(int(spec.body_type[i]), capi.Vector2(float(spec.pos[i, 0]), float(spec.pos[i, 1])),
+                                              shapes[int(spec.body_shape[i])])
+                if spec.angle[i] != 0.0:
+                    lib.frSetBodyAngle(b, float(spec.angle[i]))
+                if spec.vel[i, 0] != 0.0 or spec.vel[i, 1] != 0.0:
+                    lib.frSetBodyVelocity(b, capi.Vector2(float(spec.vel[i, 0]), float(spec.vel[i, 1])))
+                if spec.omega[i] != 0.0:
+                    lib.frSetBodyAngularVelocity(b, float(spec.omega[i]))
+                self.bodies.append(b)
+                if not lib.frxAddBodyToBatch(self.world, k, b):
+                    raise RuntimeError("frxAddBodyToBatch refused body %d of world %d" % (i, k))
+            self.ranges.append((start, len(self.bodies)))
+
+    def release(self):
+        self.lib.frReleaseWorld(self.world)
+        for s in self.shapes:
+            self.lib.frReleaseShape(s)

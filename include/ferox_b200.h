@@ -236,6 +236,15 @@ const char *frxGetLastErrorString(void);
 bool frxSetWorldCapacity(frWorld *w, int maxObjectCount);
 int frxGetWorldCapacity(const frWorld *w);
 
+/* Batched independent worlds (RL-style: thousands of small worlds): ONE device pipeline and one
+   launch set per step for all of them.  Bodies of different sub-worlds never become candidates (the
+   sub-world index is folded into the broadphase cell key); each sub-world evolves exactly as a
+   separate frWorld with the same bodies in the same order would.  frxAddBodyToBatch is deferred like
+   frAddBodyToWorld (src/world.c:147-155); frStepWorld(batch, dt) steps every sub-world. */
+frWorld *frxCreateWorldBatch(frVector2 gravity, float cellSize, int nWorlds);
+bool frxAddBodyToBatch(frWorld *batch, int worldIndex, frBody *b);
+int frxGetBatchWorldCount(const frWorld *batch);
+
 void frxSetWorldSolverMode(frWorld *w, int mode);
 int frxGetWorldSolverMode(const frWorld *w);
 /* world clock used for contact staleness (src/world.c:222-235, 362); frStepWorld never advances it */
@@ -264,6 +273,11 @@ int frxSetBodyVelocities(frWorld *w, const float *velocity, const float *angular
    receives the handles.  Returns the number of bodies accepted by the add queue. */
 int frxCreateBodies(frWorld *w, int n, const int *bodyType, const int *shapeIndex, frShape *const *shapes,
                     const float *position, const float *angle, frBody **outBodies);
+
+/* As frxCreateBodies, plus optional initial velocities and, for a batch, the sub-world of each body. */
+int frxCreateBodiesEx(frWorld *w, int n, const int *bodyType, const int *shapeIndex, frShape *const *shapes,
+                      const float *position, const float *angle, const float *velocity,
+                      const float *angularVelocity, const int *worldIndex, frBody **outBodies);
 
 /* Introspection for parity tests: the candidate pairs (world indices, first < second, plus hit flag)
    of the last step, and the contact cache as (first index, second index, frCollision) records in

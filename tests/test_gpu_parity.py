@@ -554,3 +554,54 @@ def test_capacity_growth_and_counters_at_20k_bodies(gpu):
     ow.step(1)
     assert sorted(map(tuple, fb.candidate_pairs(L, sc.world))) == sorted(map(tuple, ow.candidates()))
     sc.release(); ow.close()
+
+
+# ------------------------------------------------------------------------------------------------
+# batched independent worlds (BASELINE config 4): one launch set, per-world results unchanged
+# ------------------------------------------------------------------------------------------------
+def test_batched_worlds_equal_separate_worlds_bit_for_bit(gpu):
+    """24 small worlds (different seeds) stepped as ONE batch in reference-order mode: every
+    sub-world's bodies end up with exactly the bits the CPU oracle gives that world alone, and no
+    candidate pair ever crosses a sub-world boundary."""
+    L = gpu
+    specs = [scenes.small_world(k, n_dynamic=60) for k in range(24)]
+    oracles = []
+    for spec in specs:
+        sc = scenes.Scene(L, spec, prime=False)          # host-side set-up only: the oracle's input
+        oracles.append(orc.OracleWorld.from_scene(sc))
+    batch = scenes.BatchScene(L, specs)
+    L.frxSetWorldSolverMode(batch.world, fb.SOLVER_SERIAL)
+    L.frStepWorld(batch.world, DT)
+    assert L.frGetBodyCountInWorld(batch.world) == sum(s.n for s in specs)
+    steps = 120
+    L.frxStepWorldN(batch.world, DT, steps)
+    fb.check_error(L)
+    st = fb.body_states(L, batch.world)
+    for k, (ow, (a, b)) in enumerate(zip(oracles, batch.ranges)):
+        ow.step(steps)
+        want = ow.state()
+        for f in ("pos", "angle", "sincos", "vel", "omega", "aabb"):
+            assert_bits_equal(st[f][a:b], want[f], "world %d %s" % (k, f))
+    cands = fb.candidate_pairs(L, batch.world)
+    owner = np.zeros(len(batch.bodies), np.int32)
+    for k, (a, b) in enumerate(batch.ranges):
+        owner[a:b] = k
+    assert (owner[cands[:, 0]] == owner[cands[:, 1]]).all()
+    assert len(cands) == sum(len(ow.candidates()) for ow in oracles)
+    c = fb.step_counters(L, batch.world)
+    assert c["overflow"] == 0
+    batch.release()
+
+
+def test_batched_worlds_colored_mode_runs_many_worlds(gpu):
+    L = gpu
+    specs = [scenes.small_world(k) for k in range(256)]
+    batch = scenes.BatchScene(L, specs)
+    L.frStepWorld(batch.world, DT)
+    L.frxStepWorldN(batch.world, DT, 300)
+    fb.check_error(L)
+    st = fb.body_states(L, batch.world)
+    c = fb.step_counters(L, batch.world)
+    assert np.isfinite(st["pos"]).all() and c["overflow"] == 0 and c["bodies"] == 256 * 256
+    assert c["manifolds"] > 256 * 100
+    batch.release()
