@@ -123,6 +123,18 @@ struct frWorld_ {
     long long sticky_overflow = 0;
     long long manifold_hint = 0;
 
+    // CUDA graph of the fixed launch sequence of a step (production mode, no handler, no profiling).
+    // The kernels take DevWorld by value, so the graph is keyed on that struct + the cooperative
+    // grid size; it is (re)captured only when the key was stable for two consecutive steps.
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    DevWorld graph_key{};
+    DevWorld last_key{};
+    int graph_blocks = 0, last_blocks = 0;
+    long long graph_launches = 0;
+    bool graph_valid = false;
+    int use_graph = 1;
+
     // optional per-stage timing (frxSetProfiling): CUDA events on the world's stream around each
     // stage of every step; frxGetStageTimes sums the elapsed times
     bool profiling = false;

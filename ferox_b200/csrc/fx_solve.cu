@@ -449,7 +449,7 @@ int fx_query_coop_blocks(int device) {
     return sms * per_sm;
 }
 
-void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint) {
+int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint) {
     // A phase holds ~1/8 of the manifolds (one colour).  Fewer resident blocks make the ~100 grid
     // barriers of a solve cheaper, so take just enough blocks to give every manifold of a phase its
     // own thread, in whole multiples of the SM count, at least one block per SM.
@@ -460,6 +460,11 @@ void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int itera
     if (k > per_sm) k = per_sm;
     int blocks = (int) (k * cx.num_sms);
     if (work_hint <= 2048) blocks = (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK) < 1 ? 1 : (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK);
+    return blocks;
+}
+
+void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint) {
+    const int blocks = fx_solve_colored_blocks(cx, work_hint);
     DevWorld wc = w;
     void *args[] = { (void *) &wc, (void *) &iterations };
     cudaLaunchCooperativeKernel((const void *) k_solve_colored, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);

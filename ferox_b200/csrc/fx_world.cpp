@@ -132,6 +132,7 @@ extern "C" frWorld *frCreateWorld(frVector2 gravity, float cellSize) {
     w->cell = cellSize;
     w->capacity = default_capacity();
     ring_resize(w, w->capacity);
+    if (const char *g = std::getenv("FEROX_GRAPH")) w->use_graph = std::atoi(g);
     const char *mode = std::getenv("FEROX_SOLVER");
     if (mode && std::strcmp(mode, "serial") == 0) w->solver_mode = FRX_SOLVER_SERIAL;
     w->device_ok = world_device_init(w);
@@ -173,6 +174,7 @@ static void world_free_device(frWorld *w) {
     if (h.uid) cudaFreeHost(h.uid);
     if (h.group) cudaFreeHost(h.group);
     cudaFree(w->d_group);
+    if (w->graph_valid) { cudaGraphExecDestroy(w->graph_exec); cudaGraphDestroy(w->graph); }
     if (w->snapshot_ready) cudaEventDestroy(w->snapshot_ready);
     for (cudaEvent_t e : w->prof_events) cudaEventDestroy(e);
     for (cudaEvent_t e : w->user_events) if (e) cudaEventDestroy(e);
@@ -662,26 +664,9 @@ static void prof_mark(frWorld *w) {
     cudaEventRecord(w->prof_events[w->prof_used++], w->stream);
 }
 
-static void step_once(frWorld *w, float dt) {
+// the kernel / memset / memcpy sequence of one step on the world's stream (also what gets captured)
+static void launch_step_sequence(frWorld *w, bool collide, bool has_handler, bool serial, long long hint) {
     DevWorld &d = w->dw;
-    const bool has_handler = (w->handler.preStep != nullptr || w->handler.postStep != nullptr);
-    const bool serial = (w->solver_mode == FRX_SOLVER_SERIAL);
-    const bool collide = (w->cell > 0.0f) && !w->bodies.empty();   // NULL hash: no pairs at all
-
-    ensure_body_capacity(w, (int) w->bodies.size());
-    sync_shapes(w);
-    read_snapshot(w, false);
-    if (w->needs_sizing) {
-        world_push(w);
-        if (!sizing_prepass(w, dt)) return;
-        w->needs_sizing = false;
-    } else {
-        grow_if_crowded(w);
-    }
-    if (serial && !ensure_serial_scratch(w)) return;
-    world_push(w);
-    fill_dev_params(w, dt);
-
     prof_mark(w);
     fx_launch_begin_step(d, w->cx);
     if (serial && w->lex.zero_base) cudaMemsetAsync(w->lex.zero_base, 0, w->lex.zero_bytes, w->stream);
@@ -709,10 +694,7 @@ static void step_once(frWorld *w, float dt) {
         fx_launch_integrate_velocity(d, w->cx);                           // src/world.c:216-220
     }
     if (serial) fx_launch_solve_serial_with(d, w->cx, w->so, FR_WORLD_ITERATION_COUNT);
-    else {
-        long long hint = w->manifold_hint > (long long) w->bodies.size() ? w->manifold_hint : (long long) w->bodies.size();
-        fx_launch_solve_colored(d, w->cx, FR_WORLD_ITERATION_COUNT, hint);
-    }
+    else fx_launch_solve_colored(d, w->cx, FR_WORLD_ITERATION_COUNT, hint);
     prof_mark(w);
     fx_launch_integrate_position(d, w->cx);
     prof_mark(w);
@@ -721,6 +703,69 @@ static void step_once(frWorld *w, float dt) {
     if (has_handler) world_push(w);
     fx_launch_finish_step(d, w->cx, w->d_snapshot);
     cudaMemcpyAsync(w->h_snapshot, w->d_snapshot, sizeof(StepCountersDev), cudaMemcpyDeviceToHost, w->stream);
+}
+
+static void step_once(frWorld *w, float dt) {
+    DevWorld &d = w->dw;
+    const bool has_handler = (w->handler.preStep != nullptr || w->handler.postStep != nullptr);
+    const bool serial = (w->solver_mode == FRX_SOLVER_SERIAL);
+    const bool collide = (w->cell > 0.0f) && !w->bodies.empty();   // NULL hash: no pairs at all
+
+    ensure_body_capacity(w, (int) w->bodies.size());
+    sync_shapes(w);
+    read_snapshot(w, false);
+    if (w->needs_sizing) {
+        world_push(w);
+        if (!sizing_prepass(w, dt)) return;
+        w->needs_sizing = false;
+    } else {
+        grow_if_crowded(w);
+    }
+    if (serial && !ensure_serial_scratch(w)) return;
+    world_push(w);
+    fill_dev_params(w, dt);
+
+    const long long hint = w->manifold_hint > (long long) w->bodies.size() ? w->manifold_hint : (long long) w->bodies.size();
+    const int coop_blocks = fx_solve_colored_blocks(w->cx, hint);
+    // ---- fast path: replay the captured launch sequence ----
+    const bool graphable = w->use_graph && !has_handler && !serial && !w->profiling;
+    if (graphable) {
+        const bool same_as_last = std::memcmp(&d, &w->last_key, sizeof d) == 0 && coop_blocks == w->last_blocks;
+        w->last_key = d;
+        w->last_blocks = coop_blocks;
+        if (w->graph_valid && (std::memcmp(&d, &w->graph_key, sizeof d) != 0 || coop_blocks != w->graph_blocks)) {
+            cudaGraphExecDestroy(w->graph_exec);
+            cudaGraphDestroy(w->graph);
+            w->graph_valid = false;
+        }
+        if (!w->graph_valid && same_as_last) {
+            const long long before = g_fx_launches;
+            if (cudaStreamBeginCapture(w->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                launch_step_sequence(w, collide, has_handler, serial, hint);
+                cudaGraph_t g = nullptr;
+                if (cudaStreamEndCapture(w->stream, &g) == cudaSuccess && g != nullptr &&
+                    cudaGraphInstantiate(&w->graph_exec, g, 0) == cudaSuccess) {
+                    w->graph = g;
+                    w->graph_key = d;
+                    w->graph_blocks = coop_blocks;
+                    w->graph_launches = g_fx_launches - before;
+                    w->graph_valid = true;
+                } else {
+                    if (g) cudaGraphDestroy(g);
+                    (void) cudaGetLastError();
+                    w->use_graph = 0;                     // capture unsupported here: direct launches from now on
+                }
+                g_fx_launches = before;
+            }
+        }
+    }
+    if (graphable && w->graph_valid) {
+        cudaGraphLaunch(w->graph_exec, w->stream);
+        g_fx_launches += w->graph_launches;
+        w->device_newer = true;
+    } else {
+        launch_step_sequence(w, collide, has_handler, serial, hint);
+    }
     cudaEventRecord(w->snapshot_ready, w->stream);
     w->snapshot_pending = true;
     w->steps++;
@@ -1014,15 +1059,21 @@ extern "C" int frxGetBodyStates(frWorld *w, float *position, float *angle, float
     if (w->device_ok) cudaSetDevice(w->device);
     fx_world_pull(w);
     const int n = (int) w->bodies.size();
-    for (int i = 0; i < n; ++i) {
-        const float4 p = w->h.posrot[i], v = w->h.vel[i], a = w->h.aabb[i];
-        if (position) { position[2 * i] = p.x; position[2 * i + 1] = p.y; }
-        if (sincos) { sincos[2 * i] = p.z; sincos[2 * i + 1] = p.w; }
-        if (angle) angle[i] = w->h.angle[i];
-        if (velocity) { velocity[2 * i] = v.x; velocity[2 * i + 1] = v.y; }
-        if (angularVelocity) angularVelocity[i] = v.z;
-        if (aabb) { aabb[4 * i] = a.x; aabb[4 * i + 1] = a.y; aabb[4 * i + 2] = a.z; aabb[4 * i + 3] = a.w; }
-    }
+    const float4 *__restrict__ hp = w->h.posrot, *__restrict__ hv = w->h.vel;
+    if (position || sincos)
+        for (int i = 0; i < n; ++i) {
+            const float4 p = hp[i];
+            if (position) { position[2 * i] = p.x; position[2 * i + 1] = p.y; }
+            if (sincos) { sincos[2 * i] = p.z; sincos[2 * i + 1] = p.w; }
+        }
+    if (velocity || angularVelocity)
+        for (int i = 0; i < n; ++i) {
+            const float4 v = hv[i];
+            if (velocity) { velocity[2 * i] = v.x; velocity[2 * i + 1] = v.y; }
+            if (angularVelocity) angularVelocity[i] = v.z;
+        }
+    if (angle) std::memcpy(angle, w->h.angle, (size_t) n * sizeof(float));
+    if (aabb) std::memcpy(aabb, w->h.aabb, (size_t) n * sizeof(float4));
     return n;
 }
 
@@ -1030,11 +1081,14 @@ extern "C" int frxApplyForces(frWorld *w, const float *force, const float *torqu
     if (!w) return 0;
     fx_world_pull(w);
     if (n > (int) w->bodies.size()) n = (int) w->bodies.size();
+    float4 *__restrict__ hf = w->h.force;
+    const float4 *__restrict__ hv = w->h.vel;
     for (int i = 0; i < n; ++i) {
-        if (w->bodies[i]->inv_mass <= 0.0f) continue;          // src/rigid_body.c:300
-        float4 &f = w->h.force[i];
+        if (hv[i].w <= 0.0f) continue;                         // inverse mass, src/rigid_body.c:300
+        float4 f = hf[i];
         if (force) { f.x = f.x + force[2 * i]; f.y = f.y + force[2 * i + 1]; }
         if (torque) f.z += torque[i];
+        hf[i] = f;
     }
     w->dirty |= FX_DIRTY_FORCE;
     return n;

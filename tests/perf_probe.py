@@ -41,3 +41,15 @@ solve_b = 964.0 * M + 376.0 * Q
 print("solve alg GB/s %.1f   step alg bytes/body %.0f" % (solve_b / (st[3] / k * 1e-3) / 1e9, (N * 168 + 104 * K + Cn * 72 + 1060 * M + 376 * Q) / N))
 s = fb.body_states(L, sc.world)
 print("finite:", bool(np.isfinite(s["pos"]).all()), "max|v| %.2f" % np.abs(s["vel"]).max())
+
+# ---- end-to-end call breakdown (host buffers every step) ----
+ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+nb = L.frGetBodyCountInWorld(sc.world)
+force = np.zeros((nb, 2), np.float32); force[:, 0] = 0.01
+t_apply = t_step = t_get = 0.0
+for _ in range(30):
+    t0 = time.perf_counter(); L.frxApplyForces(sc.world, ptr(force), None, nb); t1 = time.perf_counter()
+    L.frStepWorld(sc.world, scenes.DT); t2 = time.perf_counter()
+    L.frxGetBodyStates(sc.world, ptr(s["pos"]), ptr(s["angle"]), ptr(s["sincos"]), ptr(s["vel"]), ptr(s["omega"]), ptr(s["aabb"])); t3 = time.perf_counter()
+    t_apply += t1 - t0; t_step += t2 - t1; t_get += t3 - t2
+print("e2e per step: apply %.3f ms, step(launch) %.3f ms, get(sync+D2H+copy) %.3f ms" % (t_apply / 30 * 1e3, t_step / 30 * 1e3, t_get / 30 * 1e3))
