@@ -116,6 +116,9 @@ struct DevWorld {
     unsigned int *uid;
     const int *group;    // batched worlds: sub-world index per body (nullptr: a single world)
     int n_groups;
+    const int2 *grange;  // per sub-world {first body index, body count} (host-maintained)
+    unsigned int *gcnt, *goff, *gfill;   // per sub-world manifold count / offset / fill cursor
+    unsigned int *gorder;                // manifold indices grouped by sub-world
     int *idx_of_uid;     // uid -> world index, -1 when the body left the world
     const ShapeDev *shapes;
     // broadphase scratch

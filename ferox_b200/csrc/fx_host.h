@@ -84,6 +84,14 @@ struct frWorld_ {
     int solver_mode = FRX_SOLVER_COLORED;
     int n_groups = 1;                // > 1: a batch of independent sub-worlds sharing this pipeline
     int *d_group = nullptr;
+    // block-local solve (fx_solve.cu k_solve_local): per sub-world body ranges, host-maintained
+    std::vector<int2> grange_host;
+    int2 *d_grange = nullptr;
+    unsigned int *d_gcnt = nullptr, *d_goff = nullptr, *d_gfill = nullptr, *d_gorder = nullptr;
+    int d_groups_cap = 0;
+    unsigned int d_gorder_cap = 0;
+    int local_max_bodies = 0;        // 0: not eligible (some sub-world's bodies are not one short index range)
+    int use_local = 1;
 
     HostMirror h;
     unsigned dirty = 0;

@@ -58,6 +58,8 @@ void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_ve
 void fx_launch_lexsort_candidates(const DevWorld &w, const FxLaunchCtx &cx, const FxLexScratch &lex, int body_bits);
 void fx_launch_narrowphase(const DevWorld &w, const FxLaunchCtx &cx);
 void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx);
+#define FX_LOCAL_MAX_BODIES 4096
+void fx_launch_solve_local(const DevWorld &w, const FxLaunchCtx &cx, int iterations, int max_bodies);
 int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint);
 void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint);
 void fx_launch_serial_order(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o);

@@ -133,6 +133,7 @@ extern "C" frWorld *frCreateWorld(frVector2 gravity, float cellSize) {
     w->capacity = default_capacity();
     ring_resize(w, w->capacity);
     if (const char *g = std::getenv("FEROX_GRAPH")) w->use_graph = std::atoi(g);
+    if (const char *g = std::getenv("FEROX_LOCAL_SOLVE")) w->use_local = std::atoi(g);
     const char *mode = std::getenv("FEROX_SOLVER");
     if (mode && std::strcmp(mode, "serial") == 0) w->solver_mode = FRX_SOLVER_SERIAL;
     w->device_ok = world_device_init(w);
@@ -173,7 +174,7 @@ static void world_free_device(frWorld *w) {
     if (h.shape) cudaFreeHost(h.shape);
     if (h.uid) cudaFreeHost(h.uid);
     if (h.group) cudaFreeHost(h.group);
-    cudaFree(w->d_group);
+    cudaFree(w->d_group); cudaFree(w->d_grange); cudaFree(w->d_gcnt); cudaFree(w->d_goff); cudaFree(w->d_gfill); cudaFree(w->d_gorder);
     if (w->graph_valid) { cudaGraphExecDestroy(w->graph_exec); cudaGraphDestroy(w->graph); }
     if (w->snapshot_ready) cudaEventDestroy(w->snapshot_ready);
     for (cudaEvent_t e : w->prof_events) cudaEventDestroy(e);
@@ -307,6 +308,45 @@ void fx_world_pull(frWorld *w) {
     std::memset(w->h.force, 0, n * sizeof(float4));   // cleared by the step (src/world.c:481-482)
 }
 
+// Per sub-world body index range (a plain world is one group).  The block-local solver stages a
+// group's velocities in shared memory, which needs the group's bodies in ONE short index range.
+static void update_group_ranges(frWorld *w) {
+    const int n = (int) w->bodies.size(), G = w->n_groups;
+    if (w->graph_valid) {                       // the captured sequence may pick another solver kernel now
+        cudaGraphExecDestroy(w->graph_exec);
+        cudaGraphDestroy(w->graph);
+        w->graph_valid = false;
+    }
+    w->local_max_bodies = 0;
+    if (G <= 1) {
+        if (n > 0 && n <= FX_LOCAL_MAX_BODIES) w->local_max_bodies = n;
+        return;
+    }
+    std::vector<int> lo((size_t) G, 0x7fffffff), hi((size_t) G, -1);
+    for (int i = 0; i < n; ++i) {
+        const int g = w->h.group[i];
+        if (i < lo[g]) lo[g] = i;
+        if (i > hi[g]) hi[g] = i;
+    }
+    w->grange_host.assign((size_t) G, make_int2(0, 0));
+    int worst = 0;
+    for (int g = 0; g < G; ++g) {
+        if (hi[g] < 0) continue;
+        w->grange_host[g] = make_int2(lo[g], hi[g] - lo[g] + 1);
+        if (hi[g] - lo[g] + 1 > worst) worst = hi[g] - lo[g] + 1;
+    }
+    if (G > w->d_groups_cap) {
+        dev_realloc(w->d_grange, 0, (size_t) G, w->stream, false);
+        dev_realloc(w->d_gcnt, 0, (size_t) G, w->stream, false);
+        dev_realloc(w->d_goff, 0, (size_t) G, w->stream, false);
+        dev_realloc(w->d_gfill, 0, (size_t) G, w->stream, false);
+        w->d_groups_cap = G;
+    }
+    cudaMemcpyAsync(w->d_grange, w->grange_host.data(), (size_t) G * sizeof(int2), cudaMemcpyHostToDevice, w->stream);
+    cudaStreamSynchronize(w->stream);
+    if (worst > 0 && worst <= FX_LOCAL_MAX_BODIES) w->local_max_bodies = worst;
+}
+
 static void world_push(frWorld *w) {
     const size_t n = w->bodies.size();
     cudaStream_t s = w->stream;
@@ -325,6 +365,7 @@ static void world_push(frWorld *w) {
         }
     }
     w->dirty = 0;
+    if (w->uid_dirty) update_group_ranges(w);
     if (w->uid_dirty) {
         const size_t m = w->uid_index.size();
         if ((int) m > w->d_uid_cap) {
@@ -591,6 +632,13 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.shapes = w->d_shapes;
     d.group = (w->n_groups > 1) ? w->d_group : nullptr;
     d.n_groups = w->n_groups;
+    d.grange = w->d_grange;
+    d.gcnt = w->d_gcnt; d.goff = w->d_goff; d.gfill = w->d_gfill;
+    if (w->n_groups > 1 && w->d_gorder_cap < d.cap_manifolds) {
+        dev_realloc(w->d_gorder, 0, (size_t) d.cap_manifolds, w->stream, false);
+        w->d_gorder_cap = d.cap_manifolds;
+    }
+    d.gorder = w->d_gorder;
 }
 
 static void read_snapshot(frWorld *w, bool wait) {
@@ -694,6 +742,7 @@ static void launch_step_sequence(frWorld *w, bool collide, bool has_handler, boo
         fx_launch_integrate_velocity(d, w->cx);                           // src/world.c:216-220
     }
     if (serial) fx_launch_solve_serial_with(d, w->cx, w->so, FR_WORLD_ITERATION_COUNT);
+    else if (w->use_local && w->local_max_bodies > 0) fx_launch_solve_local(d, w->cx, FR_WORLD_ITERATION_COUNT, w->local_max_bodies);
     else fx_launch_solve_colored(d, w->cx, FR_WORLD_ITERATION_COUNT, hint);
     prof_mark(w);
     fx_launch_integrate_position(d, w->cx);
