@@ -46,6 +46,12 @@ EXT_PROTOTYPES = {
     "frxCreateWorldBatch": (P, [capi.Vector2, F, I]),
     "frxAddBodyToBatch": (C.c_bool, [P, I, P]),
     "frxGetBatchWorldCount": (I, [P]),
+    "frxStripConfigure": (I, [P, F, F, F, I, C.c_uint, C.c_uint]),
+    "frxStripRegisterShapes": (I, [P, P, I]),
+    "frxStripLinkLocal": (I, [P, P]),
+    "frxStripGetNcclUniqueId": (I, [P]),
+    "frxStripInitNccl": (I, [P, I, I, P]),
+    "frxStripStep": (None, [C.POINTER(C.c_void_p), I, F]),
     "frxSetWorldSolverMode": (None, [P, I]),
     "frxGetWorldSolverMode": (I, [P]),
     "frxSetWorldTimestamp": (None, [P, F]),

@@ -61,7 +61,7 @@ __device__ __forceinline__ void integrate_position_one(const DevWorld &w, int i,
 }
 
 __global__ void __launch_bounds__(BD_BLOCK) k_integrate_position(DevWorld w) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n_owned; i += gridDim.x * blockDim.x) {
         integrate_position_one(w, i, w.dt);
         w.force[i] = make_float4(0.f, 0.f, 0.f, 0.f);    // frClearBodyForces, world.c:481-482
     }
@@ -99,8 +99,8 @@ void fx_launch_begin_step(const DevWorld &w, const FxLaunchCtx &cx) {
 }
 
 void fx_launch_integrate_position(const DevWorld &w, const FxLaunchCtx &cx) {
-    if (w.n == 0) return;
-    k_integrate_position<<<grid_for(w.n, BD_BLOCK, cx.max_blocks), BD_BLOCK, 0, cx.stream>>>(w); ++g_fx_launches;
+    if (w.n_owned == 0) return;
+    k_integrate_position<<<grid_for(w.n_owned, BD_BLOCK, cx.max_blocks), BD_BLOCK, 0, cx.stream>>>(w); ++g_fx_launches;
 }
 
 void fx_launch_finish_step(const DevWorld &w, const FxLaunchCtx &cx, StepCountersDev *snapshot) {

@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w) {
         if (cnt == 0u || cnt > FX_LARGE_CELLS) continue;
         CellRect r = body_rect(w.aabb[i], w.inv_cell);
         unsigned int pos = w.cell_off[i];
-        unsigned int massbit = (w.vel[i].w > 0.0f) ? ENT_MASS : 0u;
+        // ghost rows never count as 'has mass': ghost/ghost and ghost/static pairs belong to the owner
+        unsigned int massbit = (w.vel[i].w > 0.0f && i < w.n_owned) ? ENT_MASS : 0u;
         for (int y = r.y0; y <= r.y1; ++y)
             for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw);
     }
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_large(DevWorld w) {
         CellRect r = body_rect(w.aabb[i], w.inv_cell);
         unsigned int rw = (unsigned int) (r.x1 - r.x0 + 1);
         unsigned int cnt = w.cell_cnt[i], pos = w.cell_off[i];
-        unsigned int massbit = (w.vel[i].w > 0.0f) ? ENT_MASS : 0u;
+        unsigned int massbit = (w.vel[i].w > 0.0f && (int) i < w.n_owned) ? ENT_MASS : 0u;
         for (unsigned int t = threadIdx.x; t < cnt; t += blockDim.x)
             emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw);
     }

@@ -100,8 +100,20 @@ struct StepCountersDev {
     unsigned int pad[3];
 };
 
+// One body row as it travels between neighbouring strips of a decomposed world (96 B).
+struct __align__(16) GhostRow {
+    float4 posrot, vel, mprop, force, aabb;
+    float angle;
+    int shape_idx, shape_type;
+    unsigned int uid;
+};
+static_assert(sizeof(GhostRow) == 96, "GhostRow layout");
+// message = 16-byte header {count, 0, 0, 0} + capacity rows (fixed size: no host round trip)
+#define FX_MSG_HEADER 16
+
 struct DevWorld {
-    int n;               // bodies in the world
+    int n;               // body rows the kernels sweep (owned bodies + ghost rows in strip mode)
+    int n_owned;         // rows [0, n_owned) belong to this world; the rest are ghosts of neighbours
     int n_shapes;
     float cell, inv_cell;
     float gx, gy;

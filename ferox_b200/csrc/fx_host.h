@@ -131,6 +131,28 @@ struct frWorld_ {
     long long sticky_overflow = 0;
     long long manifold_hint = 0;
 
+    // strip decomposition of one large world (fx_strip.cu, frxStrip* in fx_world.cpp)
+    struct Strip {
+        bool enabled = false;
+        float cut_lo = 0.f, cut_hi = 0.f, margin = 0.f;
+        unsigned int ghost_cap = 0;                  // ghost rows per side
+        unsigned int uid_base = 0, uid_space = 0;    // this rank's slice of the global uid space
+        unsigned char *send_full = nullptr;          // my left-border bodies  -> left neighbour
+        unsigned char *recv_full = nullptr;          // right neighbour's left-border bodies = my ghosts
+        float4 *send_vel = nullptr, *recv_vel = nullptr;       // border velocities: -> left / <- right
+        float4 *send_delta = nullptr, *recv_delta = nullptr;   // ghost velocity changes: -> right / <- left
+        float4 *ghost_before = nullptr, *border_before = nullptr;
+        unsigned int *ghost_split = nullptr, *border_split = nullptr;   // rows that are mass-split this step
+        unsigned int *border_idx = nullptr;
+        unsigned int *ghost_cnt = nullptr;           // device word: ghost rows in use this step
+        frWorld *peer[2] = { nullptr, nullptr };     // in-process neighbours (left, right)
+        void *nccl_comm = nullptr;                   // multi-process neighbours
+        int rank = 0, nranks = 1;
+        cudaEvent_t sent = nullptr;                  // my copies into the neighbours' receive buffers are done
+        cudaEvent_t consumed = nullptr;              // I have read my receive buffers (neighbours may overwrite them)
+        bool ghosts_primed = false;
+    } strip;
+
     // CUDA graph of the fixed launch sequence of a step (production mode, no handler, no profiling).
     // The kernels take DevWorld by value, so the graph is keyed on that struct + the cooperative
     // grid size; it is (re)captured only when the key was stable for two consecutive steps.

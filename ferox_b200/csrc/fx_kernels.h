@@ -61,7 +61,7 @@ void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx);
 #define FX_LOCAL_MAX_BODIES 4096
 void fx_launch_solve_local(const DevWorld &w, const FxLaunchCtx &cx, int iterations, int max_bodies);
 int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint);
-void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint);
+void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint, int phases = 7);
 void fx_launch_serial_order(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o);
 void fx_launch_solve_serial_with(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, int iterations);
 void fx_launch_integrate_position(const DevWorld &w, const FxLaunchCtx &cx);
@@ -72,3 +72,22 @@ void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o);
 
 // single-pair / utility entry points (used by the public per-body functions and the tests)
 void fx_launch_collide_pairs(const DevWorld &w, const FxLaunchCtx &cx, const int2 *pairs, int n, Manifold *out);
+
+// strip decomposition (fx_strip.cu)
+void fx_launch_strip_pack(const DevWorld &w, const FxLaunchCtx &cx, int side, float cut, float margin, unsigned char *msg,
+                          unsigned int *border_idx, unsigned int capacity);
+void fx_launch_strip_clear_ghost_map(const DevWorld &w, const FxLaunchCtx &cx, int first_row, int rows);
+void fx_launch_strip_unpack(const DevWorld &w, const FxLaunchCtx &cx, const unsigned char *msg, int first_row, unsigned int capacity,
+                            unsigned int *ghost_cnt);
+void fx_launch_strip_mark_used(const DevWorld &w, const FxLaunchCtx &cx, float4 *flags_msg, unsigned int capacity);
+void fx_launch_strip_scale_mass(const DevWorld &w, const FxLaunchCtx &cx, const float4 *ghost_flags, unsigned int *ghost_keep, const unsigned int *ghost_cnt,
+                                const float4 *border_flags, unsigned int *border_keep, const unsigned int *border_idx, const unsigned char *full_msg,
+                                unsigned int capacity, float k, int latch);
+void fx_launch_strip_stage_begin(const DevWorld &w, const FxLaunchCtx &cx, float4 *ghost_before, const unsigned int *ghost_cnt,
+                                 const unsigned char *full_msg, const unsigned int *border_idx, float4 *border_before, unsigned int capacity);
+void fx_launch_strip_stage_pack(const DevWorld &w, const FxLaunchCtx &cx, const float4 *ghost_before, const unsigned int *ghost_split, float4 *delta,
+                                const unsigned int *ghost_cnt, const unsigned char *full_msg, const unsigned int *border_idx,
+                                const float4 *border_before, const unsigned int *border_split, float4 *border_vel, unsigned int capacity);
+void fx_launch_strip_stage_apply(const DevWorld &w, const FxLaunchCtx &cx, const unsigned char *full_msg, const unsigned int *border_idx,
+                                 const float4 *recv_delta, const float4 *recv_vel, const float4 *my_delta, const unsigned int *ghost_cnt,
+                                 unsigned int capacity);

@@ -120,7 +120,13 @@ __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, flo
     vel[b.y - lo] = make_float4(vb.x, vb.y, vb.w, vb4.w);
 }
 
-__global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iterations) {
+// `phases`: bit 0 = colouring + ordering + solver records + warm start, bit 1 = `iterations` sweeps,
+// bit 2 = write-back.  A plain step launches all three at once; a strip-decomposed world launches
+// them separately so that ghost velocities can be refreshed between sweeps.
+#define SV_SETUP 1
+#define SV_SWEEP 2
+#define SV_WRITEBACK 4
+__global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iterations, int phases) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_hist[FX_MAX_COLORS];
     __shared__ unsigned int s_off[FX_MAX_COLORS + 1];
@@ -131,6 +137,7 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
     unsigned int *color_cnt = w.color_scratch, *color_fill = w.color_scratch + FX_MAX_COLORS,
                  *color_rem = w.color_scratch + 2 * FX_MAX_COLORS;
 
+    if (phases & SV_SETUP) {
     // ---- phase 0: per-body colouring state.  Manifolds that persist from the previous step arrive
     // with the colour they had (carried through the contact cache); those colours are re-validated
     // here (a body that became dynamic may now see one colour twice) and only new manifolds go
@@ -239,13 +246,20 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
     grid.sync();
 
     // ---- phase 3: solver records + warm start, one colour at a time
-    const unsigned int ncolors = s_ncolors;
-    for (unsigned int c = 0; c < ncolors; ++c) {
+    for (unsigned int c = 0; c < s_ncolors; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
         for (unsigned int s = s_off[c] + tid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, w.vel, 0);
         grid.sync();
     }
+    } else {
+        // a later launch of the same step: the colour layout is in global memory
+        if (threadIdx.x <= FX_MAX_COLORS) s_off[threadIdx.x] = w.color_off[threadIdx.x];
+        if (threadIdx.x == 0) s_ncolors = w.ctr->n_colors;
+        __syncthreads();
+    }
+    const unsigned int ncolors = s_ncolors;
     // ---- phase 4: Gauss-Seidel sweeps
+    if (phases & SV_SWEEP)
     for (int it = 0; it < iterations; ++it)
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
             grid.sync();
         }
     // ---- phase 5: write the impulses and effective masses back to the cache
+    if (phases & SV_WRITEBACK)
     for (unsigned int s = tid; s < M; s += nth) {
         const int cs = w.sol.count_src[s];
         const unsigned int m = (unsigned int) cs >> 2;
@@ -641,10 +656,10 @@ int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint) {
     return blocks;
 }
 
-void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint) {
+void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint, int phases) {
     const int blocks = fx_solve_colored_blocks(cx, work_hint);
     DevWorld wc = w;
-    void *args[] = { (void *) &wc, (void *) &iterations };
+    void *args[] = { (void *) &wc, (void *) &iterations, (void *) &phases };
     cudaLaunchCooperativeKernel((const void *) k_solve_colored, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);
     ++g_fx_launches;
 }

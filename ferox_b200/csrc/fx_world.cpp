@@ -162,6 +162,12 @@ static void world_free_device(frWorld *w) {
     cudaFree(w->lex.keys[0]); cudaFree(w->lex.keys[1]); cudaFree(w->lex.vals[0]); cudaFree(w->lex.vals[1]);
     cudaFree(w->lex.tmp); cudaFree(w->lex.zero_base);
     cudaFree(w->so.r_key); cudaFree(w->so.r_len); cudaFree(w->so.t_key); cudaFree(w->so.t_val);
+    cudaFree(w->strip.send_full); cudaFree(w->strip.recv_full); cudaFree(w->strip.send_vel); cudaFree(w->strip.recv_vel);
+    cudaFree(w->strip.send_delta); cudaFree(w->strip.recv_delta); cudaFree(w->strip.ghost_before); cudaFree(w->strip.border_before);
+    cudaFree(w->strip.ghost_split); cudaFree(w->strip.border_split);
+    cudaFree(w->strip.border_idx); cudaFree(w->strip.ghost_cnt);
+    if (w->strip.sent) cudaEventDestroy(w->strip.sent);
+    if (w->strip.consumed) cudaEventDestroy(w->strip.consumed);
     cudaFree(w->d_snapshot);
     if (w->h_snapshot) cudaFreeHost(w->h_snapshot);
     HostMirror &h = w->h;
@@ -264,6 +270,8 @@ extern "C" float frxGetWorldTimestamp(const frWorld *w) { return w ? w->timestam
 // ---------------------------------------------------------------------------------------------
 // host mirror <-> device
 // ---------------------------------------------------------------------------------------------
+static bool rebuild_zero_region(frWorld *w);
+
 static bool ensure_body_capacity(frWorld *w, int need) {
     if (need <= w->body_cap) return true;
     int cap = w->body_cap ? w->body_cap : 1024;
@@ -284,6 +292,8 @@ static bool ensure_body_capacity(frWorld *w, int need) {
          dev_realloc(d.winner, 0, n, s, false);
     d.cap_large = (unsigned int) n;
     w->body_cap = cap;
+    // the look-back status words of the per-body sweep are sized by the body capacity
+    if (ok && w->cx.zero_base != nullptr) ok = rebuild_zero_region(w);
     return ok;
 }
 
@@ -368,15 +378,21 @@ static void world_push(frWorld *w) {
     if (w->uid_dirty) update_group_ranges(w);
     if (w->uid_dirty) {
         const size_t m = w->uid_index.size();
-        if ((int) m > w->d_uid_cap) {
-            int cap = w->d_uid_cap ? w->d_uid_cap : 1024;
-            while (cap < (int) m) cap *= 2;
+        // strip mode: uids are global (uid_base + local), the map covers the whole uid space
+        const size_t need = w->strip.enabled ? (size_t) w->strip.uid_space : m;
+        if ((long long) need > (long long) w->d_uid_cap) {
+            long long cap = w->d_uid_cap ? w->d_uid_cap : 1024;
+            while (cap < (long long) need) cap *= 2;
             dev_realloc(w->d_idx_of_uid, 0, (size_t) cap, s, false);
-            w->d_uid_cap = cap;
+            w->d_uid_cap = (int) cap;
+        }
+        if (w->strip.enabled) {
+            cudaMemsetAsync(w->d_idx_of_uid, 0xff, (size_t) w->d_uid_cap * sizeof(int), s);
+            w->strip.ghosts_primed = false;          // ghost rows are re-registered by the next unpack
         }
         if (m) {
             // pageable source: the copy is staged synchronously, which is what we want here
-            cudaMemcpyAsync(w->d_idx_of_uid, w->uid_index.data(), m * sizeof(int), cudaMemcpyHostToDevice, s);
+            cudaMemcpyAsync(w->d_idx_of_uid + w->strip.uid_base, w->uid_index.data(), m * sizeof(int), cudaMemcpyHostToDevice, s);
             cudaStreamSynchronize(s);
         }
         w->uid_dirty = false;
@@ -452,7 +468,7 @@ static void attach_body(frWorld *w, frBody *b) {
     h.posrot[i] = b->loc.posrot; h.angle[i] = b->loc.angle; h.vel[i] = b->loc.vel; h.mprop[i] = b->loc.mprop;
     h.force[i] = b->loc.force; h.aabb[i] = b->loc.aabb;
     h.shape[i] = make_int2(shape_slot(w, b->shape), b->shape ? (int) b->shape->type : 0);
-    h.uid[i] = uid;
+    h.uid[i] = w->strip.uid_base + uid;
     h.group[i] = b->group;
     b->world = w; b->index = i; b->uid = uid;
     w->bodies.push_back(b);
@@ -615,7 +631,8 @@ static bool ensure_serial_scratch(frWorld *w) {
 // ---------------------------------------------------------------------------------------------
 static void fill_dev_params(frWorld *w, float dt) {
     DevWorld &d = w->dw;
-    d.n = (int) w->bodies.size();
+    d.n_owned = (int) w->bodies.size();
+    d.n = d.n_owned + (w->strip.enabled ? (int) w->strip.ghost_cap : 0);
     d.cell = w->cell;
     d.inv_cell = (w->cell > 0.0f) ? 1.0f / w->cell : 0.0f;     // src/broad_phase.c:62-63
     d.gx = w->gravity.x;
@@ -759,6 +776,10 @@ static void step_once(frWorld *w, float dt) {
     const bool has_handler = (w->handler.preStep != nullptr || w->handler.postStep != nullptr);
     const bool serial = (w->solver_mode == FRX_SOLVER_SERIAL);
     const bool collide = (w->cell > 0.0f) && !w->bodies.empty();   // NULL hash: no pairs at all
+    if (w->strip.enabled) {
+        fx_set_error(5, "frStepWorld on a strip of a decomposed world: use frxStripStep");
+        return;
+    }
 
     ensure_body_capacity(w, (int) w->bodies.size());
     sync_shapes(w);
@@ -942,6 +963,302 @@ extern "C" void frxGetStepCounters(frWorld *w, frxStepCounters *out) {
     out->colorRounds = w->last.uncolored;
     out->steps = w->steps;
     out->overflow = w->sticky_overflow;
+}
+
+// ---------------------------------------------------------------------------------------------
+// strip decomposition of one large world (BASELINE config 5); device side in
+// fx_strip.cu.  frxStripStep drives the strips this process holds through one step:
+//   pack border bodies -> exchange -> unpack ghosts -> broadphase .. warm start
+//   -> 10 x (one Gauss-Seidel sweep -> exchange border velocities) -> write-back, integrate
+// Neighbours are either worlds of the same process (device-to-device / peer copies, used by the
+// tests on one GPU and by a single process driving several GPUs) or other ranks (NCCL send/recv over
+// NVLink, one group per exchange, stream-ordered, no host synchronisation anywhere in the step).
+// Ownership is static in this version: bodies do not migrate between strips, so `margin` has to
+// cover how far border bodies drift between two re-partitionings.
+// ---------------------------------------------------------------------------------------------
+#include <dlfcn.h>
+namespace {
+struct NcclApi {
+    struct Id { char b[128]; };                      // ncclUniqueId: 128 opaque bytes, passed by value
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, Id, int) = nullptr;
+    int (*Send)(const void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*Recv)(void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+    if (g_nccl.lib) return true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { fx_set_error(6, "libnccl.so.2 not found (strip decomposition over several processes needs NCCL)"); return false; }
+    g_nccl.lib = h;
+    *(void **) &g_nccl.GetUniqueId = dlsym(h, "ncclGetUniqueId");
+    *(void **) &g_nccl.CommInitRank = dlsym(h, "ncclCommInitRank");
+    *(void **) &g_nccl.Send = dlsym(h, "ncclSend");
+    *(void **) &g_nccl.Recv = dlsym(h, "ncclRecv");
+    *(void **) &g_nccl.GroupStart = dlsym(h, "ncclGroupStart");
+    *(void **) &g_nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
+    *(void **) &g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+    *(void **) &g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
+    return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
+}
+bool nccl_ok(int rc, const char *what) {
+    if (rc == 0) return true;
+    char buf[200];
+    std::snprintf(buf, sizeof buf, "%s: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error");
+    fx_set_error(2000 + rc, buf);
+    return false;
+}
+size_t full_bytes(const frWorld *w) { return FX_MSG_HEADER + (size_t) w->strip.ghost_cap * sizeof(GhostRow); }
+size_t vel_bytes(const frWorld *w) { return (size_t) w->strip.ghost_cap * sizeof(float4); }
+}   // namespace
+
+extern "C" int frxStripGetNcclUniqueId(void *out128) {
+    if (!out128 || !nccl_load()) return -1;
+    return nccl_ok(g_nccl.GetUniqueId(out128), "ncclGetUniqueId") ? 0 : -1;
+}
+
+extern "C" int frxStripConfigure(frWorld *w, float cutLo, float cutHi, float margin, int ghostCapacity, unsigned int uidBase,
+                                 unsigned int uidSpace) {
+    if (!w || !w->device_ok || ghostCapacity <= 0 || !w->bodies.empty() || w->ring_head != w->ring_tail) return -1;
+    cudaSetDevice(w->device);
+    frWorld_::Strip &st = w->strip;
+    st.enabled = true;
+    st.cut_lo = cutLo; st.cut_hi = cutHi; st.margin = margin;
+    st.ghost_cap = (unsigned int) ghostCapacity;
+    st.uid_base = uidBase; st.uid_space = uidSpace;
+    bool ok = fx_cuda_ok(cudaMalloc((void **) &st.send_full, full_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.recv_full, full_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.send_vel, vel_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.recv_vel, vel_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.send_delta, vel_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.recv_delta, vel_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.ghost_before, vel_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.border_before, vel_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.ghost_split, (size_t) st.ghost_cap * sizeof(unsigned int)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.border_split, (size_t) st.ghost_cap * sizeof(unsigned int)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.border_idx, (size_t) st.ghost_cap * sizeof(unsigned int)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.ghost_cnt, sizeof(unsigned int)), "cudaMalloc strip");
+    if (ok) {
+        cudaMemsetAsync(st.send_full, 0, full_bytes(w), w->stream);
+        cudaMemsetAsync(st.recv_full, 0, full_bytes(w), w->stream);     // count 0 until a neighbour writes
+        cudaMemsetAsync(st.send_vel, 0, vel_bytes(w), w->stream);
+        cudaMemsetAsync(st.recv_vel, 0, vel_bytes(w), w->stream);
+        cudaMemsetAsync(st.send_delta, 0, vel_bytes(w), w->stream);
+        cudaMemsetAsync(st.recv_delta, 0, vel_bytes(w), w->stream);
+        cudaMemsetAsync(st.ghost_cnt, 0, sizeof(unsigned int), w->stream);
+        cudaMemsetAsync(st.ghost_split, 0, (size_t) st.ghost_cap * sizeof(unsigned int), w->stream);
+        cudaMemsetAsync(st.border_split, 0, (size_t) st.ghost_cap * sizeof(unsigned int), w->stream);
+    }
+    cudaEventCreateWithFlags(&st.sent, cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&st.consumed, cudaEventDisableTiming);
+    cudaEventRecord(st.consumed, w->stream);
+    w->uid_dirty = true;
+    w->use_graph = 0;
+    w->use_local = 0;
+    return ok ? 0 : -1;
+}
+
+// Ghost rows carry shape-table indices, so every strip must number its shapes identically: register
+// the complete shape list, in the same order, on every strip before adding bodies.
+extern "C" int frxStripRegisterShapes(frWorld *w, frShape *const *shapes, int n) {
+    if (!w || !w->strip.enabled || !shapes || n < 0 || !w->shape_list.empty()) return -1;
+    for (int i = 0; i < n; ++i)
+        if (shapes[i] == nullptr || shape_slot(w, shapes[i]) != i) return -1;
+    return 0;
+}
+
+extern "C" int frxStripLinkLocal(frWorld *left, frWorld *right) {
+    if (!left || !right || !left->strip.enabled || !right->strip.enabled || left->strip.ghost_cap != right->strip.ghost_cap) return -1;
+    left->strip.peer[1] = right;
+    right->strip.peer[0] = left;
+    if (left->device != right->device) {
+        int can = 0;
+        cudaDeviceCanAccessPeer(&can, left->device, right->device);
+        if (can) {
+            cudaSetDevice(left->device); cudaDeviceEnablePeerAccess(right->device, 0);
+            cudaSetDevice(right->device); cudaDeviceEnablePeerAccess(left->device, 0);
+            (void) cudaGetLastError();
+        }
+    }
+    return 0;
+}
+
+extern "C" int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *uniqueId128) {
+    if (!w || !w->strip.enabled || !uniqueId128 || !nccl_load()) return -1;
+    cudaSetDevice(w->device);
+    NcclApi::Id id;
+    std::memcpy(&id, uniqueId128, sizeof id);
+    w->strip.rank = rank;
+    w->strip.nranks = nranks;
+    return nccl_ok(g_nccl.CommInitRank(&w->strip.nccl_comm, nranks, id, rank), "ncclCommInitRank") ? 0 : -1;
+}
+
+// one exchange round for all local strips.  kind 0: border bodies go LEFT.  kind 1: border
+// velocities go LEFT and ghost velocity changes go RIGHT.
+static void strip_exchange(frWorld **ws, int n, int kind) {
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        frWorld_::Strip &st = w->strip;
+        cudaSetDevice(w->device);
+        const size_t bytes = kind == 0 ? full_bytes(w) : vel_bytes(w);
+        const void *to_left = kind == 0 ? (const void *) st.send_full : (const void *) st.send_vel;
+        void *from_right = kind == 0 ? (void *) st.recv_full : (void *) st.recv_vel;
+        if (st.nccl_comm) {
+            const int left = st.rank - 1, right = st.rank + 1;
+            g_nccl.GroupStart();
+            if (left >= 0) g_nccl.Send(to_left, bytes, /* ncclChar */ 0, left, st.nccl_comm, w->stream);
+            if (right < st.nranks) g_nccl.Recv(from_right, bytes, 0, right, st.nccl_comm, w->stream);
+            if (kind == 1) {
+                if (right < st.nranks) g_nccl.Send(st.send_delta, bytes, 0, right, st.nccl_comm, w->stream);
+                if (left >= 0) g_nccl.Recv(st.recv_delta, bytes, 0, left, st.nccl_comm, w->stream);
+            }
+            nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd");
+        } else {
+            for (int side = 0; side < 2; ++side)
+                if (st.peer[side]) cudaStreamWaitEvent(w->stream, st.peer[side]->strip.consumed, 0);   // previous message was read
+            if (frWorld *p = st.peer[0])
+                cudaMemcpyPeerAsync(kind == 0 ? (void *) p->strip.recv_full : (void *) p->strip.recv_vel, p->device, to_left, w->device, bytes, w->stream);
+            if (kind == 1)
+                if (frWorld *p = st.peer[1]) cudaMemcpyPeerAsync(p->strip.recv_delta, p->device, st.send_delta, w->device, bytes, w->stream);
+            cudaEventRecord(st.sent, w->stream);
+        }
+    }
+    // in-process neighbours: a strip may only read its receive buffers after both neighbours wrote them
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        if (w->strip.nccl_comm) continue;
+        cudaSetDevice(w->device);
+        for (int side = 0; side < 2; ++side)
+            if (w->strip.peer[side]) cudaStreamWaitEvent(w->stream, w->strip.peer[side]->strip.sent, 0);
+    }
+}
+
+// after a solver stage: trade velocity changes / fresh border velocities and reconcile both copies
+static void strip_stage_sync(frWorld **ws, int n) {
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        cudaSetDevice(w->device);
+        frWorld_::Strip &st = w->strip;
+        fx_launch_strip_stage_pack(w->dw, w->cx, st.ghost_before, st.ghost_split, st.send_delta, st.ghost_cnt, st.send_full, st.border_idx,
+                                   st.border_before, st.border_split, st.send_vel, st.ghost_cap);
+    }
+    strip_exchange(ws, n, 1);
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        cudaSetDevice(w->device);
+        frWorld_::Strip &st = w->strip;
+        fx_launch_strip_stage_apply(w->dw, w->cx, st.send_full, st.border_idx, st.recv_delta, st.recv_vel, st.send_delta, st.ghost_cnt, st.ghost_cap);
+        cudaEventRecord(st.consumed, w->stream);
+    }
+}
+
+extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
+    if (!ws || n <= 0 || dt <= 0.0f) return;
+    for (int k = 0; k < n; ++k)
+        if (!ws[k] || !ws[k]->strip.enabled || !ws[k]->device_ok) { fx_set_error(5, "frxStripStep: world is not a configured strip"); return; }
+    // ---- host-side preparation, then pack the bodies at the left cut
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        cudaSetDevice(w->device);
+        frWorld_::Strip &st = w->strip;
+        const int rows = (int) w->bodies.size() + (int) st.ghost_cap;
+        ensure_body_capacity(w, rows);
+        sync_shapes(w);
+        read_snapshot(w, false);
+        world_push(w);
+        fill_dev_params(w, dt);
+        if (!st.ghosts_primed) {
+            // make every ghost row inert once (and after every rebuild of the uid map)
+            cudaMemsetAsync(st.recv_full, 0, FX_MSG_HEADER, w->stream);
+            fx_launch_strip_unpack(w->dw, w->cx, st.recv_full, w->dw.n_owned, st.ghost_cap, st.ghost_cnt);
+            st.ghosts_primed = true;
+        }
+        if (w->cx.zero_base == nullptr && !ensure_work_capacity(w, 8ull * rows + 4096, 16ull * rows + 4096, 4ull * rows + 4096)) return;
+        fill_dev_params(w, dt);
+        const bool has_left = st.peer[0] != nullptr || (st.nccl_comm && st.rank > 0);
+        if (has_left) fx_launch_strip_pack(w->dw, w->cx, 0, st.cut_lo, st.margin, st.send_full, st.border_idx, st.ghost_cap);
+    }
+    strip_exchange(ws, n, 0);
+    // ---- ghosts in, then everything up to and including the warm start
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        cudaSetDevice(w->device);
+        frWorld_::Strip &st = w->strip;
+        DevWorld &d = w->dw;
+        fx_launch_strip_clear_ghost_map(d, w->cx, d.n_owned, (int) st.ghost_cap);
+        fx_launch_strip_unpack(d, w->cx, st.recv_full, d.n_owned, st.ghost_cap, st.ghost_cnt);
+        cudaEventRecord(st.consumed, w->stream);
+        if (w->needs_sizing) {
+            if (!sizing_prepass(w, dt)) return;
+            w->needs_sizing = false;
+        } else {
+            grow_if_crowded(w);
+        }
+        fill_dev_params(w, dt);
+        fx_launch_begin_step(d, w->cx);
+        if (w->cell > 0.0f && d.n > 0) {
+            fx_launch_broadphase(d, w->cx, true);
+            fx_launch_narrowphase(d, w->cx);
+        } else {
+            fx_launch_integrate_velocity(d, w->cx);
+        }
+        fx_launch_cache_update(d, w->cx);
+        // tell the owner which of its border bodies got a manifold here (flags ride in the delta message)
+        fx_launch_strip_mark_used(d, w->cx, st.send_delta, st.ghost_cap);
+    }
+    strip_exchange(ws, n, 1);
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        cudaSetDevice(w->device);
+        frWorld_::Strip &st = w->strip;
+        DevWorld &d = w->dw;
+        // mass splitting: both copies of a body with a cross-cut manifold get twice the inverse mass / inertia
+        fx_launch_strip_scale_mass(d, w->cx, st.send_delta, st.ghost_split, st.ghost_cnt, st.recv_delta, st.border_split, st.border_idx,
+                                   st.send_full, st.ghost_cap, 2.0f, 1);
+        cudaEventRecord(st.consumed, w->stream);
+        const long long hint = w->manifold_hint > (long long) d.n ? w->manifold_hint : (long long) d.n;
+        fx_launch_strip_stage_begin(d, w->cx, st.ghost_before, st.ghost_cnt, st.send_full, st.border_idx, st.border_before, st.ghost_cap);
+        fx_launch_solve_colored(d, w->cx, 0, hint, 1 /* set-up + warm start */);
+    }
+    strip_stage_sync(ws, n);
+    // ---- Gauss-Seidel sweeps, both copies of every border body reconciled after each
+    for (int it = 0; it < FR_WORLD_ITERATION_COUNT; ++it) {
+        for (int k = 0; k < n; ++k) {
+            frWorld *w = ws[k];
+            cudaSetDevice(w->device);
+            frWorld_::Strip &st = w->strip;
+            const long long hint = w->manifold_hint > (long long) w->dw.n ? w->manifold_hint : (long long) w->dw.n;
+            fx_launch_strip_stage_begin(w->dw, w->cx, st.ghost_before, st.ghost_cnt, st.send_full, st.border_idx, st.border_before, st.ghost_cap);
+            fx_launch_solve_colored(w->dw, w->cx, 1, hint, 2 /* one sweep */);
+        }
+        strip_stage_sync(ws, n);
+    }
+    // ---- write-back, position integration of the owned bodies, bookkeeping
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        cudaSetDevice(w->device);
+        DevWorld &d = w->dw;
+        const long long hint = w->manifold_hint > (long long) d.n ? w->manifold_hint : (long long) d.n;
+        fx_launch_solve_colored(d, w->cx, 0, hint, 4 /* write-back */);
+        frWorld_::Strip &st = w->strip;
+        fx_launch_strip_scale_mass(d, w->cx, st.send_delta, st.ghost_split, st.ghost_cnt, st.recv_delta, st.border_split, st.border_idx,
+                                   st.send_full, st.ghost_cap, 0.5f, 0);          // restore the true inverse masses
+        fx_launch_integrate_position(d, w->cx);
+        w->device_newer = true;
+        fx_launch_finish_step(d, w->cx, w->d_snapshot);
+        cudaMemcpyAsync(w->h_snapshot, w->d_snapshot, sizeof(StepCountersDev), cudaMemcpyDeviceToHost, w->stream);
+        cudaEventRecord(w->snapshot_ready, w->stream);
+        w->snapshot_pending = true;
+        w->steps++;
+        fx_cuda_ok(cudaGetLastError(), "strip step launch");
+        if (w->ring_head != w->ring_tail) drain_queue(w);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1242,6 +1559,7 @@ static Scratch *scratch() {
     cudaMallocHost((void **) &s.hcol, sizeof(CollisionPod)); cudaMallocHost((void **) &s.hout, sizeof(Manifold));
     d.shapes = s.d_shapes;
     d.n = 2;
+    d.n_owned = 2;
     { const char *e = std::getenv("FEROX_NARROWPHASE"); d.narrow_mode = (e && std::strcmp(e, "group8") == 0) ? 1 : 0; }
     s.cx.stream = s.stream;
     s.cx.max_blocks = 148 * 8;

@@ -421,3 +421,72 @@ class BatchScene:
         self.lib.frReleaseWorld(self.world)
         for s in self.shapes:
             self.lib.frReleaseShape(s)
+
+
+class StripScene:
+    """One SceneSpec cut into vertical strips, each strip a frWorld of the product (frxStrip*): dynamic
+    and kinematic bodies go to the strip whose x-interval holds their position, static bodies to every
+    strip.  All strips live in this process (in-process neighbour links) unless `rank` is given, in
+    which case only strip `rank` is built (NCCL neighbours, one process per GPU)."""
+
+    def __init__(self, lib, spec, cuts, margin=4.0, ghost_cap=4096, rank=None, devices=None):
+        self.lib, self.spec = lib, spec
+        edges = [-math.inf] + [float(c) for c in cuts] + [math.inf]
+        self.n_strips = len(edges) - 1
+        self.local = list(range(self.n_strips)) if rank is None else [rank]
+        stride = spec.n + 64
+        owner = np.searchsorted(np.asarray(cuts, np.float32), spec.pos[:, 0], side="right")
+        self.worlds, self.bodies, self.owned = [], {}, {}
+        for k in self.local:
+            if devices is not None:
+                lib.frxSetDevice(devices[k])
+            w = lib.frCreateWorld(capi.Vector2(*spec.gravity), spec.cell)
+            lib.frxSetWorldCapacity(w, spec.n + 16)
+            rc = lib.frxStripConfigure(w, edges[k], edges[k + 1], margin, ghost_cap, k * stride, self.n_strips * stride)
+            assert rc == 0, "frxStripConfigure failed"
+            shapes = [make_shape(lib, s) for s in spec.shapes]
+            arr = (C.c_void_p * len(shapes))(*shapes)
+            assert lib.frxStripRegisterShapes(w, arr, len(shapes)) == 0
+            mine = []
+            for i in range(spec.n):
+                static = int(spec.body_type[i]) == capi.BODY_STATIC
+                if not static and owner[i] != k:
+                    continue
+                b = lib.frCreateBodyFromShape(int(spec.body_type[i]), capi.Vector2(float(spec.pos[i, 0]), float(spec.pos[i, 1])),
+                                              shapes[int(spec.body_shape[i])])
+                if spec.angle[i] != 0.0:
+                    lib.frSetBodyAngle(b, float(spec.angle[i]))
+                if spec.vel[i, 0] != 0.0 or spec.vel[i, 1] != 0.0:
+                    lib.frSetBodyVelocity(b, capi.Vector2(float(spec.vel[i, 0]), float(spec.vel[i, 1])))
+                if spec.omega[i] != 0.0:
+                    lib.frSetBodyAngularVelocity(b, float(spec.omega[i]))
+                assert lib.frAddBodyToWorld(w, b)
+                self.bodies[(k, i)] = b
+                mine.append(i)
+            self.worlds.append(w)
+            self.owned[k] = np.array(mine, np.int64)
+        if rank is None:
+            for a, b in zip(self.worlds[:-1], self.worlds[1:]):
+                assert lib.frxStripLinkLocal(a, b) == 0
+        self._arr = (C.c_void_p * len(self.worlds))(*self.worlds)
+
+    def step(self, n=1, dt=DT):
+        for _ in range(n):
+            self.lib.frxStripStep(self._arr, len(self.worlds), dt)
+
+    def gather_states(self):
+        """body state of every non-static body, indexed like the spec (owned strips only)."""
+        import ferox_b200 as fb
+        n = self.spec.n
+        out = {"pos": np.full((n, 2), np.nan, np.float32), "vel": np.full((n, 2), np.nan, np.float32),
+               "angle": np.full(n, np.nan, np.float32), "omega": np.full(n, np.nan, np.float32)}
+        for w, k in zip(self.worlds, self.local):
+            st = fb.body_states(self.lib, w)
+            idx = self.owned[k]
+            for f in out:
+                out[f][idx] = st[f]
+        return out
+
+    def release(self):
+        for w in self.worlds:
+            self.lib.frReleaseWorld(w)

@@ -279,6 +279,25 @@ int frxCreateBodiesEx(frWorld *w, int n, const int *bodyType, const int *shapeIn
                       const float *position, const float *angle, const float *velocity,
                       const float *angularVelocity, const int *worldIndex, frBody **outBodies);
 
+/* Strip decomposition of ONE large world over several GPUs (BASELINE config 5).
+   Each strip is a frWorld that owns the bodies added to it; frxStripConfigure (on the still-empty
+   world) gives it the x-interval [cutLo, cutHi) it is responsible for (use -INFINITY / INFINITY at the
+   ends), the border `margin` (bodies whose AABB reaches within `margin` of a cut are mirrored on the
+   neighbour as ghosts: at least one cell plus the largest body extent plus the expected drift), the
+   ghost capacity per side and this strip's slice [uidBase, ...) of a global id space of uidSpace ids.
+   Static bodies that span cuts must be added to every strip.  Ghost rows carry shape-table indices:
+   call frxStripRegisterShapes with the complete shape list, in the same order, on every strip.  Neighbours are linked either in-process (frxStripLinkLocal: tests, or one
+   process driving several GPUs) or across processes with NCCL (frxStripGetNcclUniqueId on rank 0,
+   broadcast the 128 bytes, frxStripInitNccl everywhere).  frxStripStep advances all strips of this
+   process by one step; frStepWorld is refused on a strip.  Ownership is static in this version. */
+int frxStripConfigure(frWorld *w, float cutLo, float cutHi, float margin, int ghostCapacity, unsigned int uidBase,
+                      unsigned int uidSpace);
+int frxStripRegisterShapes(frWorld *w, frShape *const *shapes, int n);   /* same list, same order, on every strip */
+int frxStripLinkLocal(frWorld *left, frWorld *right);
+int frxStripGetNcclUniqueId(void *out128);
+int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *uniqueId128);
+void frxStripStep(frWorld **worlds, int nLocal, float dt);
+
 /* Introspection for parity tests: the candidate pairs (world indices, first < second, plus hit flag)
    of the last step, and the contact cache as (first index, second index, frCollision) records in
    the order the solver visits them.  Each returns the number of records available; at most `max`

@@ -1,0 +1,84 @@
+"""GPU: strip decomposition of one world (frxStrip*, SURVEY.md section 8e / BASELINE config 5) with
+in-process neighbours on ONE GPU: the same pack / ghost / per-sweep velocity-refresh code path that
+the NCCL transport drives across GPUs.  Cross-cut pairs are solved on both strips with ghost
+velocities refreshed once per sweep (block-Jacobi coupling across a cut), so the comparison with the
+undivided world is statistical, like the coloured-vs-serial comparison."""
+import numpy as np
+import pytest
+
+import ferox_b200 as fb
+from ferox_b200 import capi, scenes
+
+pytestmark = pytest.mark.gpu
+DT = scenes.DT
+
+
+def undivided(L, spec, steps):
+    sc = scenes.Scene(L, spec, prime=False)
+    L.frStepWorld(sc.world, DT)
+    L.frxStepWorldN(sc.world, DT, steps)
+    st = fb.body_states(L, sc.world)
+    c = fb.step_counters(L, sc.world)
+    sc.release()
+    return st, c
+
+
+def test_strips_with_no_interaction_across_the_cut_match_the_single_world(gpu):
+    """Two piles far from the cut: no ghost ever interacts, every strip must evolve exactly like the
+    same bodies in one world as far as the pair set and contact geometry go, and end within the
+    ordering tolerance (colours differ because manifold indices differ)."""
+    L = gpu
+    a = scenes.mixed_pile(400, width=30.0, seed=5)
+    spec = scenes.mixed_pile(400, width=30.0, seed=5)
+    # second pile shifted 200 units to the right, merged into one spec
+    b = scenes.mixed_pile(400, width=30.0, seed=6)
+    b.pos = b.pos + np.array([200.0, 0.0], np.float32)
+    spec.shapes = a.shapes + b.shapes
+    spec.body_type = np.concatenate([a.body_type, b.body_type])
+    spec.body_shape = np.concatenate([a.body_shape, b.body_shape + len(a.shapes)])
+    spec.pos = np.concatenate([a.pos, b.pos]); spec.angle = np.concatenate([a.angle, b.angle])
+    spec.vel = np.concatenate([a.vel, b.vel]); spec.omega = np.concatenate([a.omega, b.omega])
+    ss = scenes.StripScene(L, spec, cuts=[100.0], margin=4.0, ghost_cap=256)
+    ss.step(1)                                  # priming
+    ss.step(600)
+    fb.check_error(L)
+    got = ss.gather_states()
+    want, _ = undivided(L, spec, 600)
+    dyn = spec.body_type != capi.BODY_STATIC
+    assert np.isfinite(got["pos"][dyn]).all()
+    my, wy = got["pos"][dyn, 1].mean(), want["pos"][dyn, 1].mean()
+    assert abs(my - wy) < 0.02 * abs(wy) + 0.05, (my, wy)
+    assert got["pos"][dyn, 1].max() < 0.6
+    for w in ss.worlds:
+        assert fb.step_counters(L, w)["overflow"] == 0
+    ss.release()
+
+
+def test_two_and_three_strips_through_a_pile_match_the_single_world_statistically(gpu):
+    L = gpu
+    spec = scenes.mixed_pile(3000, width=100.0)
+    want, wc = undivided(L, spec, 600)
+    dyn = spec.body_type != capi.BODY_STATIC
+    masses = None
+    for cuts in ([50.0], [33.0, 66.0]):
+        ss = scenes.StripScene(L, spec, cuts=cuts, margin=5.0, ghost_cap=1024)
+        ss.step(1)
+        ss.step(600)
+        fb.check_error(L)
+        got = ss.gather_states()
+        assert np.isfinite(got["pos"][dyn]).all(), cuts
+        ctrs = [fb.step_counters(L, w) for w in ss.worlds]
+        assert all(c["overflow"] == 0 for c in ctrs)
+        # every dynamic body is owned exactly once
+        assert sum(len(ss.owned[k]) for k in ss.local) - (~dyn).sum() * len(ss.worlds) == dyn.sum()
+        # pile height / potential energy and kinetic energy level agree with the undivided world
+        my, wy = got["pos"][dyn, 1].mean(), want["pos"][dyn, 1].mean()
+        assert abs(my - wy) < 0.02 * abs(wy) + 0.05, (cuts, my, wy)
+        assert got["pos"][dyn, 1].max() < 0.6                      # nothing fell through the floor (top at y = 0)
+        ke_s = (got["vel"][dyn] ** 2).sum(1).mean()
+        ke_w = (want["vel"][dyn] ** 2).sum(1).mean()
+        assert ke_s < 4.0 * ke_w + 1.0, (cuts, ke_s, ke_w)
+        # manifolds: each cross-cut manifold exists on both strips, so the sum is a little larger
+        m = sum(c["manifolds"] for c in ctrs)
+        assert wc["manifolds"] * 0.97 < m < wc["manifolds"] * 1.25, (cuts, m, wc["manifolds"])
+        ss.release()
