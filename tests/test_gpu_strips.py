@@ -1,8 +1,14 @@
 """GPU: strip decomposition of one world (frxStrip*, SURVEY.md section 8e / BASELINE config 5) with
-in-process neighbours on ONE GPU: the same pack / ghost / per-sweep velocity-refresh code path that
-the NCCL transport drives across GPUs.  Cross-cut pairs are solved on both strips with ghost
-velocities refreshed once per sweep (block-Jacobi coupling across a cut), so the comparison with the
-undivided world is statistical, like the coloured-vs-serial comparison."""
+in-process neighbours on ONE GPU: the same pack / ghost / per-stage reconciliation code path that
+the NCCL transport drives across GPUs (the last test launches that one, two processes, when the box
+has two GPUs).  Cross-cut pairs are solved on the left strip only; velocity changes of ghosts are
+returned to their owner after every solver stage (Jacobi coupling across a cut, mass-split), so the
+comparison with the undivided world is statistical, like the coloured-vs-serial comparison."""
+import json
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 
@@ -78,7 +84,25 @@ def test_two_and_three_strips_through_a_pile_match_the_single_world_statisticall
         ke_s = (got["vel"][dyn] ** 2).sum(1).mean()
         ke_w = (want["vel"][dyn] ** 2).sum(1).mean()
         assert ke_s < 4.0 * ke_w + 1.0, (cuts, ke_s, ke_w)
-        # manifolds: each cross-cut manifold exists on both strips, so the sum is a little larger
+        # manifolds: a cross-cut manifold exists on the left strip only; stale ghost entries add a few
         m = sum(c["manifolds"] for c in ctrs)
         assert wc["manifolds"] * 0.97 < m < wc["manifolds"] * 1.25, (cuts, m, wc["manifolds"])
         ss.release()
+
+
+def test_two_strips_on_two_gpus_over_nccl(gpu):
+    """One process per GPU, the library's own NCCL send/recv between neighbours (tests/strip_ranks.py)."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29541", os.path.join(root, "tests", "strip_ranks.py"), "--bodies", "3000", "--steps", "600"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    r = json.loads(line)
+    assert r["finite"] and r["overflow"] == 0 and r["bodies"] == r["dynamic"], r
+    assert abs(r["mean_y"] - r["mean_y_single"]) < 0.02 * abs(r["mean_y_single"]) + 0.05, r
+    assert r["max_y"] < 0.6 and r["ke"] < 4.0 * r["ke_single"] + 1.0, r
+    assert r["manifolds_single"] * 0.97 < r["manifolds"] < r["manifolds_single"] * 1.25, r
