@@ -48,15 +48,42 @@ def parse_args():
     ap.add_argument("--bodies", type=int, default=65536)
     ap.add_argument("--settle", type=int, default=600)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config2", choices=["config2", "config4"],
-                    help="config2 (default, the headline): one 65,536-body mixed pile per GPU; config4: 4,096 "
-                         "independent 256-body worlds batched into one launch set and sharded over the GPUs")
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
+                    help="config2 (default, the headline): one 65,536-body mixed pile per GPU; config3: one 1M-circle column "
+                         "collapse per GPU; config4: 4,096 independent 256-body worlds batched into one launch set and "
+                         "sharded over the GPUs; config5: ONE pile of N x 1,048,576 bodies cut into N strips, one per GPU, "
+                         "NCCL ghost-body exchange between neighbours")
     ap.add_argument("--worlds", type=int, default=4096)
-    return ap.parse_args()
+    ap.add_argument("--margin", type=float, default=5.0, help="config5: ghost margin either side of a cut")
+    ap.add_argument("--ghost-cap", type=int, default=8192, help="config5: ghost rows per cut")
+    a = ap.parse_args()
+    if a.workload in ("config3", "config5") and a.bodies == 65536:
+        a.bodies = 1048576
+    return a
 
 
 def workload_name(n):
     return "config2: %d mixed circles + convex polygons (3-8 verts) pile + 3 static walls, cell 2.0, dt 1/60" % n
+
+
+def build_bulk_world(L, spec):
+    """One world from a SceneSpec through the bulk-creation call (1M bodies in well under a second)."""
+    from ferox_b200 import capi, scenes
+    world = L.frCreateWorld(capi.Vector2(*spec.gravity), spec.cell)
+    L.frxSetWorldCapacity(world, spec.n + 16)
+    shapes = (C.c_void_p * len(spec.shapes))(*[scenes.make_shape(L, s) for s in spec.shapes])
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    pos, ang = np.ascontiguousarray(spec.pos, np.float32), np.ascontiguousarray(spec.angle, np.float32)
+    got = L.frxCreateBodiesEx(world, spec.n, np.ascontiguousarray(spec.body_type, np.int32), np.ascontiguousarray(spec.body_shape, np.int32),
+                              shapes, pos.reshape(-1), ptr(ang), None, None, None, None)
+    assert got == spec.n, (got, spec.n)
+
+    class World:
+        pass
+    b = World()
+    b.world, b.lib = world, L
+    b.release = lambda: L.frReleaseWorld(world)
+    return b
 
 
 def build_config4_batch(L, n_worlds, rank, world_size):
@@ -230,27 +257,53 @@ def run_b200(args):
         raise SystemExit("no CUDA device %d: the ferox world step has no CPU fallback" % local_rank)
 
     dt = scenes.DT
-    if args.workload == "config4":
-        sc = build_config4_batch(L, args.worlds, rank, world_size)
-        L.frStepWorld(sc.world, dt)
-        n = L.frGetBodyCountInWorld(sc.world)
-    else:
-        spec = scenes.mixed_pile(args.bodies, seed=1234 + rank)
-        sc = scenes.Scene(L, spec, prime=False)
-        L.frStepWorld(sc.world, dt)                  # priming step: queued bodies enter the world
-        n = L.frGetBodyCountInWorld(sc.world)
-        assert n == spec.n, (n, spec.n)
-    L.frxStepWorldN(sc.world, dt, args.settle)       # settle the pile (untimed)
-    L.frxSynchronizeWorld(sc.world)
-    fb.check_error(L)
-
-    warm = max(3, args.warmup)
-    L.frxStepWorldN(sc.world, dt, warm)
-    L.frxSynchronizeWorld(sc.world)
+    strips = args.workload == "config5"
 
     def barrier():
         if dist is not None:
             dist.barrier()
+
+    if args.workload == "config4":
+        sc = build_config4_batch(L, args.worlds, rank, world_size)
+        L.frStepWorld(sc.world, dt)
+        n = L.frGetBodyCountInWorld(sc.world)
+    elif strips:
+        spec, lo, hi = scenes.strip_pile(args.bodies, rank, world_size, storeys=8)
+        sc = scenes.StripScene.local(L, spec, rank, world_size, lo, hi, margin=args.margin, ghost_cap=args.ghost_cap, device=local_rank)
+        sc.world = sc.worlds[0]
+        if world_size > 1:
+            import torch
+            uid = torch.zeros(128, dtype=torch.uint8)
+            if rank == 0:
+                buf = (C.c_ubyte * 128)()
+                assert L.frxStripGetNcclUniqueId(buf) == 0, L.frxGetLastErrorString()
+                uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+            uid = uid.to(torch.device("cuda", local_rank))
+            dist.broadcast(uid, 0)
+            assert L.frxStripInitNccl(sc.world, rank, world_size, uid.cpu().numpy().tobytes()) == 0, L.frxGetLastErrorString()
+        sc.step(1)
+        n = L.frGetBodyCountInWorld(sc.world)
+        assert n == spec.n, (n, spec.n)
+    else:
+        spec = scenes.column_collapse(args.bodies, cols=max(512, args.bodies // 96), pitch=1.2, jitter=0.2, floor_width=32768.0) if args.workload == "config3" else scenes.mixed_pile(args.bodies, seed=1234 + rank)
+        sc = scenes.Scene(L, spec, prime=False) if args.workload == "config2" else build_bulk_world(L, spec)
+        L.frStepWorld(sc.world, dt)                  # priming step: queued bodies enter the world
+        n = L.frGetBodyCountInWorld(sc.world)
+        assert n == spec.n, (n, spec.n)
+
+    def step_n(k):
+        if strips:
+            sc.step(k)
+        else:
+            L.frxStepWorldN(sc.world, dt, k)
+
+    step_n(args.settle)                              # settle the pile (untimed)
+    L.frxSynchronizeWorld(sc.world)
+    fb.check_error(L)
+
+    warm = max(3, args.warmup)
+    step_n(warm)
+    L.frxSynchronizeWorld(sc.world)
 
     # ---- timed region A: device-resident state, per-step CUDA events, cold L2 ----
     sampler = ClockSampler(local_rank)
@@ -262,7 +315,15 @@ def run_b200(args):
     ncu_range = os.environ.get("FEROX_NCU_RANGE") == "1"     # `ncu --profile-from-start off` captures only this span
     if ncu_range:
         L.frxProfilerRange(1)
-    L.frxTimedSteps(sc.world, dt, args.steps, 1, ms)
+    if strips:
+        # per-step brackets would serialise the ranks; one bracket around K steps on this strip's stream.
+        # The per-step working set (> 2 GB for 1M bodies) is far larger than the 126 MB L2.
+        L.frxRecordEvent(sc.world, 0)
+        sc.step(args.steps)
+        L.frxRecordEvent(sc.world, 1)
+        ms[:] = float(L.frxEventElapsedMs(sc.world, 0, 1)) / args.steps
+    else:
+        L.frxTimedSteps(sc.world, dt, args.steps, 1, ms)
     if ncu_range:
         L.frxProfilerRange(0)
     clocks = sampler.stop()
@@ -277,7 +338,7 @@ def run_b200(args):
 
     # back-to-back (warm L2, no per-step bracket) for context
     L.frxRecordEvent(sc.world, 0)
-    L.frxStepWorldN(sc.world, dt, args.steps)
+    step_n(args.steps)
     L.frxRecordEvent(sc.world, 1)
     warm_ms = float(L.frxEventElapsedMs(sc.world, 0, 1))
 
@@ -292,7 +353,10 @@ def run_b200(args):
     checksum = 0.0
     for _ in range(e2e_steps):
         L.frxApplyForces(sc.world, ptr(force), None, n)            # host -> pinned mirror, H2D in the step
-        L.frStepWorld(sc.world, dt)
+        if strips:
+            sc.step(1)
+        else:
+            L.frStepWorld(sc.world, dt)
         L.frxGetBodyStates(sc.world, ptr(st["pos"]), ptr(st["angle"]), ptr(st["sincos"]), ptr(st["vel"]),
                            ptr(st["omega"]), ptr(st["aabb"]))       # D2H + host copy of every body state
         checksum += float(st["pos"][0, 1])
@@ -323,25 +387,39 @@ def run_b200(args):
         solve_ms = solve_ms_total / max(1, prof_steps)
         achieved = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
         step_bytes = (n * (160 + 2 * 24) + 104 * ctr["cellEntries"] + ctr["candidates"] * (64 + 92) + 1060 * M + 376 * Q)
+        roof_kernel = "k_solve_colored"
+        if strips:
+            # the strip step runs the solver as 12 separately launched stages with an exchange after each; there
+            # are no per-stage events, so the roofline line is the WHOLE step of this rank's strip
+            solve_bytes, solve_ms, roof_kernel = float(step_bytes), elapsed_ms / args.steps, "whole strip step (all kernels + exchanges)"
+            achieved = solve_bytes / (solve_ms * 1e-3) / 1e9
+        names = {"config2": workload_name(args.bodies),
+                 "config3": "config3: %d-circle granular column collapse (r 0.5, loose lattice of 96 rows x %d columns, right side free) "
+                            "+ floor + wall, cell 2.0, dt 1/60" % (args.bodies, max(512, args.bodies // 96)),
+                 "config4": "config4: %d independent worlds x 256 bodies (252 dynamic mixed + floor + 2 walls + kinematic paddle), "
+                            "batched into one launch set per GPU" % args.worlds,
+                 "config5": "config5: ONE pile of %d x %d mixed bodies on 8 storeys, cut into %d vertical strips (1 per GPU), "
+                            "ghost margin %.1f" % (world_size, args.bodies, world_size, args.margin)}
+        par = {"config2": "independent worlds, 1 per GPU", "config3": "independent worlds, 1 per GPU",
+               "config4": "worlds sharded round-robin over the GPUs, no communication",
+               "config5": "strip domain decomposition, per-stage NCCL send/recv of ghost rows / velocity changes between neighbours"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": warm,
             "ms_per_step": elapsed_ms / args.steps, "higher_is_better": True,
             "scaling": "strong" if args.workload == "config4" else "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": workload_name(args.bodies) if args.workload == "config2" else
-                       "config4: %d independent worlds x 256 bodies (252 dynamic mixed + floor + 2 walls + kinematic paddle), "
-                       "batched into one launch set per GPU" % args.worlds,
+            "config": {"workload": names[args.workload],
                        "bodies_per_gpu": n, "settle_steps": args.settle,
                        "solver": "graph-coloured PGS, 10 iterations",
-                       "parallelism": "independent worlds, 1 per GPU" if args.workload == "config2" else
-                       "worlds sharded round-robin over the GPUs, no communication",
-                       "l2": "flushed between timed steps (256 MiB memset on the step's stream, outside the event bracket)",
+                       "parallelism": par[args.workload],
+                       "l2": "per-step working set (> 2 GB) exceeds the 126 MB L2; one event bracket around the K steps" if strips else
+                             "flushed between timed steps (256 MiB memset on the step's stream, outside the event bracket)",
                        "counters": ctr},
             "value_warm_l2": total_bodies * args.steps / (warm_ms * 1e-3),
             "stage_ms_per_step": {k: stage_ms[i] / max(1, prof_steps) for i, k in
                                   enumerate(["broadphase", "narrowphase", "cache", "solve", "integrate"])},
             "step_algorithmic_GBps": step_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
-            "roofline": {"bound": "hbm", "kernel": "k_solve_colored", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_launch": solve_bytes, "ms_per_launch": solve_ms},
             "e2e": {"value": total_bodies * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 16),

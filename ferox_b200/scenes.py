@@ -171,9 +171,65 @@ def mixed_pile(n=65536, seed=1234, width=None, pitch=1.7, shared_shapes=False, m
 
 
 # --------------------------------------------------------------------------------------------------
+# config 5: one wide mixed pile, generated strip by strip (second row)
+# --------------------------------------------------------------------------------------------------
+def strip_pile_shapes(strip_width, height):
+    """The shape table every strip of a strip_pile registers (same list, same order): floor segment,
+    end wall, circle, regular 3..8-gons."""
+    shapes = [ShapeSpec("rect", (strip_width + 128.0, 2.0)), ShapeSpec("rect", (2.0, height + 2.0)), ShapeSpec("circle", (0.5,))]
+    for nv in range(3, 9):
+        rad = _poly_radius(nv)
+        shapes.append(ShapeSpec("poly", tuple((rad * math.cos(2.0 * math.pi * j / nv), rad * math.sin(2.0 * math.pi * j / nv))
+                                              for j in range(nv))))
+    return shapes
+
+
+def strip_pile(per_strip, k, n_strips, seed=1234, pitch=1.7, max_rows=96, storeys=1):
+    """Strip k of ONE pile of n_strips * per_strip dynamic bodies (50 % circles, 50 % regular 3..8-gons
+    at random angles) resting on `storeys` floors stacked vertically, each pile at most `max_rows`
+    lattice rows deep (see mixed_pile; several storeys keep an 8M-body world narrow enough for
+    float32 positions: 8 x 1M bodies on 8 storeys is 18.6k units wide, ulp 0.002).  The strip covers x
+    in [k W, (k+1) W); its static bodies are its own floor segments (overlapping the neighbours' by 64
+    units, statics are never ghosted) and the end wall(s) of the whole pile.
+    Returns (spec, cut_lo, cut_hi)."""
+    per_storey = (per_strip + storeys - 1) // storeys
+    per_row = max(8, int(math.ceil(per_storey / max_rows)))
+    width = per_row * pitch
+    n_rows = (per_storey + per_row - 1) // per_row
+    storey_h = n_rows * pitch + 40.0
+    height = storeys * storey_h
+    spec = SceneSpec(name="config5_strip_pile_%dx%d" % (n_strips, per_strip), cell=2.0)
+    spec.shapes = strip_pile_shapes(width, height)
+    x0 = k * width
+    u = splitmix_uniform(seed + 7919 * k, 4 * per_strip).reshape(per_strip, 4)
+    i = np.arange(per_strip)
+    storey, j = i // per_storey, i % per_storey
+    row, col = j // per_row, j % per_row
+    x = x0 + pitch * (col + 0.25 + 0.5 * (row & 1) * 0.5) + 0.05 * (u[:, 0] - 0.5)
+    y = -1.0 - pitch * row - 0.05 * u[:, 1] - storey * storey_h
+    shape = np.where(u[:, 2] < 0.5, 2, 3 + np.minimum((u[:, 2] - 0.5) * 12.0, 5.0).astype(np.int64))
+    ang = u[:, 3] * 2.0 * math.pi
+    types, shapes, pos, angle = [], [], [], []
+    for f in range(storeys):
+        types.append(capi.BODY_STATIC); shapes.append(0); pos.append((x0 + 0.5 * width, 1.0 - f * storey_h)); angle.append(0.0)
+    if k == 0:
+        types.append(capi.BODY_STATIC); shapes.append(1); pos.append((-1.0, -height * 0.5 + 1.0)); angle.append(0.0)
+    if k == n_strips - 1:
+        types.append(capi.BODY_STATIC); shapes.append(1); pos.append((n_strips * width + 1.0, -height * 0.5 + 1.0)); angle.append(0.0)
+    ns = len(types)
+    spec = _finish(spec, np.concatenate([np.array(types, np.int32), np.full(per_strip, capi.BODY_DYNAMIC, np.int32)]),
+                   np.concatenate([np.array(shapes, np.int64), shape]),
+                   np.concatenate([np.array(pos, np.float64).reshape(ns, 2), np.stack([x, y], 1)]),
+                   np.concatenate([np.array(angle, np.float64), ang]))
+    lo = -math.inf if k == 0 else x0
+    hi = math.inf if k == n_strips - 1 else x0 + width
+    return spec, lo, hi
+
+
+# --------------------------------------------------------------------------------------------------
 # config 3: granular column collapse, uniform circles (SURVEY.md section 8d "Config 3")
 # --------------------------------------------------------------------------------------------------
-def column_collapse(n=1048576, cols=512, seed=1, floor_width=16384.0, pitch=1.05):
+def column_collapse(n=1048576, cols=512, seed=1, floor_width=16384.0, pitch=1.05, jitter=0.02):
     spec = SceneSpec(name="config3_column_collapse_%d" % n, cell=2.0)
     rows = (n + cols - 1) // cols
     spec.shapes = [
@@ -184,8 +240,8 @@ def column_collapse(n=1048576, cols=512, seed=1, floor_width=16384.0, pitch=1.05
     k = np.arange(n)
     row, col = k // cols, k % cols
     u = splitmix_uniform(seed, 2 * n)
-    x = 0.5 + pitch * col + 0.02 * (u[0::2] - 0.5)
-    y = -0.5 - pitch * row + 0.02 * (u[1::2] - 0.5) - 0.01
+    x = 0.5 + pitch * col + jitter * (u[0::2] - 0.5)
+    y = -0.5 - pitch * row + jitter * (u[1::2] - 0.5) - 0.5 * jitter
     pos = np.empty((n + 2, 2), np.float64)
     # floor top edge at y = 0, left wall right edge at x = 0; the right wall is "removed at t = 0"
     pos[0] = (floor_width * 0.5 - 64.0, 1.0)
@@ -469,6 +525,30 @@ class StripScene:
             for a, b in zip(self.worlds[:-1], self.worlds[1:]):
                 assert lib.frxStripLinkLocal(a, b) == 0
         self._arr = (C.c_void_p * len(self.worlds))(*self.worlds)
+
+    @classmethod
+    def local(cls, lib, spec, k, n_strips, cut_lo, cut_hi, margin=4.0, ghost_cap=4096, device=None):
+        """Strip k only, from a spec that already holds just this strip's bodies (strip_pile); bodies
+        are created in bulk.  Neighbours are linked by the caller (frxStripInitNccl)."""
+        self = cls.__new__(cls)
+        self.lib, self.spec, self.n_strips, self.local = lib, spec, n_strips, [k]
+        if device is not None:
+            lib.frxSetDevice(device)
+        stride = spec.n + 64
+        w = lib.frCreateWorld(capi.Vector2(*spec.gravity), spec.cell)
+        lib.frxSetWorldCapacity(w, spec.n + 16)
+        assert lib.frxStripConfigure(w, cut_lo, cut_hi, margin, ghost_cap, k * stride, n_strips * stride) == 0
+        shapes = [make_shape(lib, s) for s in spec.shapes]
+        arr = (C.c_void_p * len(shapes))(*shapes)
+        assert lib.frxStripRegisterShapes(w, arr, len(shapes)) == 0
+        ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+        bt, bs = np.ascontiguousarray(spec.body_type, np.int32), np.ascontiguousarray(spec.body_shape, np.int32)
+        pos, ang = np.ascontiguousarray(spec.pos, np.float32), np.ascontiguousarray(spec.angle, np.float32)
+        got = lib.frxCreateBodiesEx(w, spec.n, bt, bs, arr, pos.reshape(-1), ptr(ang), None, None, None, None)
+        assert got == spec.n, (got, spec.n)
+        self.worlds, self.bodies, self.owned = [w], {}, {k: np.arange(spec.n, dtype=np.int64)}
+        self._arr = (C.c_void_p * 1)(w)
+        return self
 
     def step(self, n=1, dt=DT):
         for _ in range(n):
