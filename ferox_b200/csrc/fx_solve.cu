@@ -134,6 +134,10 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
     const ManifoldSet man = w.man[*w.cur_flip];
     const unsigned int M = w.ctr->n_manifolds;
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // per-colour loops: consecutive WARPS go to different blocks, so that a colour with fewer manifolds
+    // than the grid has threads keeps a few warps busy on every SM instead of filling the first blocks
+    // only; a warp still reads 32 consecutive records ([measured] solve 0.357 -> 0.338 ms at 65k bodies)
+    const unsigned int vtid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u);
     unsigned int *color_cnt = w.color_scratch, *color_fill = w.color_scratch + FX_MAX_COLORS,
                  *color_rem = w.color_scratch + 2 * FX_MAX_COLORS;
 
@@ -248,7 +252,7 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
     // ---- phase 3: solver records + warm start, one colour at a time
     for (unsigned int c = 0; c < s_ncolors; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
-        for (unsigned int s = s_off[c] + tid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, w.vel, 0);
+        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, w.vel, 0);
         grid.sync();
     }
     } else {
@@ -263,7 +267,7 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
     for (int it = 0; it < iterations; ++it)
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
-            for (unsigned int s = s_off[c] + tid; s < s_off[c + 1]; s += nth) sweep_one(w, s, w.vel, 0);
+            for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one(w, s, w.vel, 0);
             grid.sync();
         }
     // ---- phase 5: write the impulses and effective masses back to the cache
