@@ -348,29 +348,42 @@ def run_b200(args):
     ptr = lambda a: a.ctypes.data_as(C.c_void_p)
     st = fb.body_states(L, sc.world)
     e2e_steps = max(10, min(args.steps, 100))
-    barrier()
-    t0 = time.perf_counter()
-    checksum = 0.0
-    for _ in range(e2e_steps):
-        L.frxApplyForces(sc.world, ptr(force), None, n)            # host -> pinned mirror, H2D in the step
-        if strips:
-            sc.step(1)
-        else:
-            L.frStepWorld(sc.world, dt)
-        L.frxGetBodyStates(sc.world, ptr(st["pos"]), ptr(st["angle"]), ptr(st["sincos"]), ptr(st["vel"]),
-                           ptr(st["omega"]), ptr(st["aabb"]))       # D2H + host copy of every body state
-        checksum += float(st["pos"][0, 1])
-    L.frxSynchronizeWorld(sc.world)
-    e2e_s = time.perf_counter() - t0
-    barrier()
+    f32p = C.POINTER(C.c_float)
+    vp, va, vv, vb = f32p(), f32p(), f32p(), f32p()
+
+    def e2e_loop(copy_out):
+        """per step: forces from a host array (H2D), one step, every body state back in host memory (D2H)."""
+        barrier()
+        t0 = time.perf_counter()
+        acc = 0.0
+        for _ in range(e2e_steps):
+            L.frxApplyForces(sc.world, ptr(force), None, n)            # host -> pinned mirror, H2D in the step
+            if strips:
+                sc.step(1)
+            else:
+                L.frStepWorld(sc.world, dt)
+            if copy_out:
+                L.frxGetBodyStates(sc.world, ptr(st["pos"]), ptr(st["angle"]), ptr(st["sincos"]), ptr(st["vel"]),
+                                   ptr(st["omega"]), ptr(st["aabb"]))   # D2H + re-layout into the caller's arrays
+                acc += float(st["pos"][0, 1])
+            else:
+                L.frxViewBodyStates(sc.world, C.byref(vp), C.byref(va), C.byref(vv), C.byref(vb))   # D2H into the pinned mirror
+                acc += float(vp[1]) + float(vv[4 * (n - 1)]) + float(vb[4 * (n // 2)]) + float(va[n // 3])
+        L.frxSynchronizeWorld(sc.world)
+        secs = time.perf_counter() - t0
+        barrier()
+        return secs, acc
+
+    e2e_s, checksum = e2e_loop(False)
+    e2e_copy_s, _ = e2e_loop(True)
     fb.check_error(L)
 
     # ---- max over ranks ----
     if dist is not None:
         import torch
         from ferox_b200 import sharding
-        elapsed_ms, total_bodies, (warm_ms, e2e_s, solve_ms_total) = sharding.reduce_report(
-            dist, torch.device("cuda", local_rank), elapsed_ms, n, extra_max=(warm_ms, e2e_s, stage_ms[3]))
+        elapsed_ms, total_bodies, (warm_ms, e2e_s, solve_ms_total, e2e_copy_s) = sharding.reduce_report(
+            dist, torch.device("cuda", local_rank), elapsed_ms, n, extra_max=(warm_ms, e2e_s, stage_ms[3], e2e_copy_s))
     else:
         solve_ms_total = float(stage_ms[3])
         total_bodies = n
@@ -423,7 +436,10 @@ def run_b200(args):
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
                          "bytes_per_launch": solve_bytes, "ms_per_launch": solve_ms},
             "e2e": {"value": total_bodies * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 16),
-                    "d2h_bytes_per_step": int(n * 52), "steps": e2e_steps, "checksum": checksum},
+                    "d2h_bytes_per_step": int(n * 52), "steps": e2e_steps, "checksum": checksum,
+                    "api": "frxApplyForces + frStepWorld + frxViewBodyStates (states land in the library's pinned host mirror)",
+                    "value_copy_out": total_bodies * e2e_steps / e2e_copy_s,
+                    "api_copy_out": "same with frxGetBodyStates (re-laid out into 6 caller-owned pageable arrays)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

@@ -60,6 +60,7 @@ EXT_PROTOTYPES = {
     "frxSynchronizeWorld": (None, [P]),
     "frxGetStepCounters": (None, [P, C.POINTER(StepCounters)]),
     "frxGetBodyStates": (I, [P, P, P, P, P, P, P]),
+    "frxViewBodyStates": (I, [P, P, P, P, P]),
     "frxApplyForces": (I, [P, P, P, I]),
     "frxSetBodyVelocities": (I, [P, P, P, I]),
     "frxCreateBodies": (I, [P, I, i32p, i32p, P, f32p, P, P]),
@@ -125,6 +126,18 @@ def body_states(L, world):
     L.frxGetBodyStates(world, ptr(out["pos"]), ptr(out["angle"]), ptr(out["sincos"]), ptr(out["vel"]),
                        ptr(out["omega"]), ptr(out["aabb"]))
     return out
+
+
+def body_state_views(L, world):
+    """Zero-copy numpy views of the pinned host mirror (valid until the world is stepped or edited)."""
+    f32p = C.POINTER(C.c_float)
+    p, a, v, b = f32p(), f32p(), f32p(), f32p()
+    n = L.frxViewBodyStates(world, C.byref(p), C.byref(a), C.byref(v), C.byref(b))
+    if n == 0:
+        z = np.zeros((0, 4), np.float32)
+        return {"posrot": z, "angle": np.zeros(0, np.float32), "vel": z, "aabb": z}
+    arr = lambda ptr, shape: np.ctypeslib.as_array(ptr, shape=shape)
+    return {"posrot": arr(p, (n, 4)), "angle": arr(a, (n,)), "vel": arr(v, (n, 4)), "aabb": arr(b, (n, 4))}
 
 
 def candidate_pairs(L, world):

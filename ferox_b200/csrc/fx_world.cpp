@@ -1443,6 +1443,17 @@ extern "C" int frxGetBodyStates(frWorld *w, float *position, float *angle, float
     return n;
 }
 
+extern "C" int frxViewBodyStates(frWorld *w, const float **posRot, const float **angle, const float **velocity, const float **aabb) {
+    if (!w) return 0;
+    if (w->device_ok) cudaSetDevice(w->device);
+    fx_world_pull(w);
+    if (posRot) *posRot = reinterpret_cast<const float *>(w->h.posrot);
+    if (angle) *angle = w->h.angle;
+    if (velocity) *velocity = reinterpret_cast<const float *>(w->h.vel);
+    if (aabb) *aabb = reinterpret_cast<const float *>(w->h.aabb);
+    return (int) w->bodies.size();
+}
+
 extern "C" int frxApplyForces(frWorld *w, const float *force, const float *torque, int n) {
     if (!w) return 0;
     fx_world_pull(w);

@@ -263,6 +263,11 @@ void frxGetStepCounters(frWorld *w, frxStepCounters *out);
    angularVelocity float[n], aabb float[n][4], force float[n][2], torque float[n]. */
 int frxGetBodyStates(frWorld *w, float *position, float *angle, float *sincos, float *velocity,
                      float *angularVelocity, float *aabb);
+/* Zero-copy variant: downloads the state once (if the device is ahead) and returns READ-ONLY views of
+   the library's pinned host mirror, valid until the next call that steps or edits the world:
+   posRot float[n][4] = (x, y, sin, cos), angle float[n], velocity float[n][4] = (vx, vy, omega,
+   1/mass), aabb float[n][4] = (x, y, w, h).  This is what the per-body getters read.  Returns n. */
+int frxViewBodyStates(frWorld *w, const float **posRot, const float **angle, const float **velocity, const float **aabb);
 /* adds force/torque to every body with inverse mass > 0, like n frApplyForceToBody calls at the
    body's centre plus a pure torque (src/rigid_body.c:299-306) */
 int frxApplyForces(frWorld *w, const float *force, const float *torque, int n);

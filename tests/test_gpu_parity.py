@@ -605,3 +605,23 @@ def test_batched_worlds_colored_mode_runs_many_worlds(gpu):
     assert np.isfinite(st["pos"]).all() and c["overflow"] == 0 and c["bodies"] == 256 * 256
     assert c["manifolds"] > 256 * 100
     batch.release()
+
+
+def test_state_views_equal_the_copying_getter(gpu):
+    """frxViewBodyStates exposes the pinned host mirror itself: same numbers as frxGetBodyStates and the
+    per-body getters, refreshed after every step."""
+    L = gpu
+    spec = scenes.mixed_pile(2000, width=80.0)
+    sc = scenes.Scene(L, spec, prime=False)
+    L.frStepWorld(sc.world, DT)
+    for _ in range(3):
+        L.frxStepWorldN(sc.world, DT, 40)
+        v = fb.body_state_views(L, sc.world)
+        st = fb.body_states(L, sc.world)
+        assert np.array_equal(v["posrot"][:, :2], st["pos"]) and np.array_equal(v["posrot"][:, 2:], st["sincos"])
+        assert np.array_equal(v["vel"][:, :2], st["vel"]) and np.array_equal(v["vel"][:, 2], st["omega"])
+        assert np.array_equal(v["angle"], st["angle"]) and np.array_equal(v["aabb"], st["aabb"])
+        p = L.frGetBodyPosition(sc.bodies[7])
+        assert (p.x, p.y) == (float(v["posrot"][7, 0]), float(v["posrot"][7, 1]))
+    fb.check_error(L)
+    sc.release()
