@@ -437,7 +437,7 @@ def run_b200(args):
                          "bytes_per_launch": solve_bytes, "ms_per_launch": solve_ms},
             "e2e": {"value": total_bodies * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 16),
                     "d2h_bytes_per_step": int(n * 52), "steps": e2e_steps, "checksum": checksum,
-                    "api": "frxApplyForces + frStepWorld + frxViewBodyStates (states land in the library's pinned host mirror)",
+                    "api": "frxApplyForces + frStepWorld (frxStripStep on a strip) + frxViewBodyStates (states land in the library's pinned host mirror)",
                     "value_copy_out": total_bodies * e2e_steps / e2e_copy_s,
                     "api_copy_out": "same with frxGetBodyStates (re-laid out into 6 caller-owned pageable arrays)"},
             "gpu_launches": int(launches),
