@@ -15,7 +15,7 @@ from . import capi
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB_PATH = os.path.join(HERE, "_build", "libferox.so")
+LIB_PATH = os.environ.get("FEROX_B200_LIB") or os.path.join(HERE, "_build", "libferox.so")   # env: A/B builds in dev probes
 
 SOLVER_COLORED, SOLVER_SERIAL = 0, 1
 

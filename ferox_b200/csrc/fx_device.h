@@ -79,10 +79,10 @@ struct SolverSet {
     float4 *nt;      // {n.x, n.y, t.x, t.y}
     float4 *mat;     // {friction, restitution, invInertiaA, invInertiaB}
     int *count_src;  // count | (source manifold index << 2)
-    float4 *r;       // [2*cap] {r1.x, r1.y, r2.x, r2.y}
-    float4 *u;       // [2*cap] {u1.x, u1.y, u2.x, u2.y}   unit left-normals of r1, r2
-    float4 *k;       // [2*cap] {bias, normalMass, tangentMass, 0}
-    float2 *lam;     // [2*cap] {normalScalar, tangentScalar}
+    float4 *r;       // [2][cap] contact-major: {r1.x, r1.y, r2.x, r2.y}
+    float4 *u;       // [2][cap] {u1.x, u1.y, u2.x, u2.y}   unit left-normals of r1, r2
+    float4 *k;       // [2][cap] {bias, normalMass, tangentMass, 0}
+    float2 *lam;     // [2][cap] {normalScalar, tangentScalar}
 };
 
 struct StepCountersDev {
@@ -151,6 +151,7 @@ struct DevWorld {
     unsigned int *h_val;
     // solver
     SolverSet sol;
+    unsigned int sol_stride, sol_mult;   // per-contact record (slot s, contact c) lives at c * sol_stride + s * sol_mult
     unsigned int *order;                 // manifold indices grouped by colour
     unsigned int *color_off;             // [FX_MAX_COLORS + 1]
     unsigned long long *body_mask;       // colours already used by each body

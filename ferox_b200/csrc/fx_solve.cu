@@ -35,6 +35,12 @@ extern long long g_fx_launches;
 namespace cg = cooperative_groups;
 
 #define SV_BLOCK 256
+// per-contact solver records: slot-major [slot][2] for small worlds (the rare second contact of a slot shares the
+// sector of the first, so its load is an L1 hit inside a latency-bound phase) or CONTACT-MAJOR [2][slot] for
+// large ones (93 % of the manifolds of a pile carry one contact, Q/M = 1.07: side by side, every sweep dragged
+// the unused second 16 bytes of each sector through HBM).  [measured] contact-major: solve 2.48 -> 2.25 ms at
+// 1 M bodies, 0.334 -> 0.352 ms at 65 k; the host picks per world size (fill_dev_params).
+#define SOL_AT(w, s, c) ((size_t) (c) * (size_t) (w).sol_stride + (size_t) (s) * (size_t) (w).sol_mult)
 
 __device__ __forceinline__ unsigned int ticket_of(unsigned int m, unsigned int round) {
     // bijection on 26 bits (odd multipliers and xor-shifts are invertible), so tickets are unique
@@ -87,37 +93,50 @@ __device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const 
         k.bias = contact_bias(g.z, w.inv_dt);
         contact_masses(k, n, t, inv_ma, inv_mb, inv_ia, inv_ib);
         contact_warm_start(k, n, t, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
-        w.sol.r[2 * s + c] = make_float4(k.r1.x, k.r1.y, k.r2.x, k.r2.y);
-        w.sol.u[2 * s + c] = make_float4(k.u1.x, k.u1.y, k.u2.x, k.u2.y);
-        w.sol.k[2 * s + c] = make_float4(k.bias, k.nmass, k.tmass, 0.0f);
-        w.sol.lam[2 * s + c] = make_float2(im.y, im.w);
+        w.sol.r[SOL_AT(w, s, c)] = make_float4(k.r1.x, k.r1.y, k.r2.x, k.r2.y);
+        w.sol.u[SOL_AT(w, s, c)] = make_float4(k.u1.x, k.u1.y, k.u2.x, k.u2.y);
+        w.sol.k[SOL_AT(w, s, c)] = make_float4(k.bias, k.nmass, k.tmass, 0.0f);
+        w.sol.lam[SOL_AT(w, s, c)] = make_float2(im.y, im.w);
     }
     vel[b.x - lo] = make_float4(va.x, va.y, va.w, inv_ma);
     vel[b.y - lo] = make_float4(vb.x, vb.y, vb.w, inv_mb);
 }
 
 __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, float4 *vel, int lo) {
+    // level 1: everything addressed by the slot alone, issued together
     const int cs = w.sol.count_src[s];
-    const int count = cs & 3;
-    if (count == 0) return;
     const int2 b = w.sol.body[s];
     const float4 nt = w.sol.nt[s];
     const float4 mat = w.sol.mat[s];
+    const float4 r0 = w.sol.r[SOL_AT(w, s, 0)], u0 = w.sol.u[SOL_AT(w, s, 0)], k0 = w.sol.k[SOL_AT(w, s, 0)];
+    float2 l0 = w.sol.lam[SOL_AT(w, s, 0)];
+    const int count = cs & 3;
+    if (count == 0) return;
+    // level 2: the velocities (addressed through b) and, for the few two-contact manifolds, the second record
     float4 va4 = vel[b.x - lo], vb4 = vel[b.y - lo];
+    float4 r1 = r0, u1 = u0, k1 = k0;
+    float2 l1 = l0;
+    if (count > 1) {
+        r1 = w.sol.r[SOL_AT(w, s, 1)]; u1 = w.sol.u[SOL_AT(w, s, 1)]; k1 = w.sol.k[SOL_AT(w, s, 1)];
+        l1 = w.sol.lam[SOL_AT(w, s, 1)];
+    }
     Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
     const V2 n = v2(nt.x, nt.y), t = v2(nt.z, nt.w);
-    for (int c = 0; c < count; ++c) {
-        const float4 r = w.sol.r[2 * s + c], u = w.sol.u[2 * s + c], kk = w.sol.k[2 * s + c];
-        float2 lam = w.sol.lam[2 * s + c];
-        ContactK k;
-        k.r1 = v2(r.x, r.y); k.r2 = v2(r.z, r.w);
-        k.u1 = v2(u.x, u.y); k.u2 = v2(u.z, u.w);
-        k.bias = kk.x; k.nmass = kk.y; k.tmass = kk.z;
-        contact_resolve(k, n, t, mat.x, mat.y, lam.x, lam.y, va4.w, vb4.w, mat.z, mat.w, va, vb);
-        w.sol.lam[2 * s + c] = lam;
+    ContactK k;
+    k.r1 = v2(r0.x, r0.y); k.r2 = v2(r0.z, r0.w);
+    k.u1 = v2(u0.x, u0.y); k.u2 = v2(u0.z, u0.w);
+    k.bias = k0.x; k.nmass = k0.y; k.tmass = k0.z;
+    contact_resolve(k, n, t, mat.x, mat.y, l0.x, l0.y, va4.w, vb4.w, mat.z, mat.w, va, vb);
+    if (count > 1) {
+        k.r1 = v2(r1.x, r1.y); k.r2 = v2(r1.z, r1.w);
+        k.u1 = v2(u1.x, u1.y); k.u2 = v2(u1.z, u1.w);
+        k.bias = k1.x; k.nmass = k1.y; k.tmass = k1.z;
+        contact_resolve(k, n, t, mat.x, mat.y, l1.x, l1.y, va4.w, vb4.w, mat.z, mat.w, va, vb);
     }
     vel[b.x - lo] = make_float4(va.x, va.y, va.w, va4.w);
     vel[b.y - lo] = make_float4(vb.x, vb.y, vb.w, vb4.w);
+    w.sol.lam[SOL_AT(w, s, 0)] = l0;
+    if (count > 1) w.sol.lam[SOL_AT(w, s, 1)] = l1;
 }
 
 // `phases`: bit 0 = colouring + ordering + solver records + warm start, bit 1 = `iterations` sweeps,
@@ -277,8 +296,8 @@ __global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iter
         const unsigned int m = (unsigned int) cs >> 2;
         const int count = cs & 3;
         for (int c = 0; c < count; ++c) {
-            float4 kk = w.sol.k[2 * s + c];
-            float2 lam = w.sol.lam[2 * s + c];
+            float4 kk = w.sol.k[SOL_AT(w, s, c)];
+            float2 lam = w.sol.lam[SOL_AT(w, s, c)];
             man.imp[2 * m + c] = make_float4(kk.y, lam.x, kk.z, lam.y);
         }
     }
@@ -453,8 +472,8 @@ __global__ void k_solve_local(DevWorld w, int iterations, int max_bodies) {
             const unsigned int m = (unsigned int) cs >> 2;
             const int count = cs & 3;
             for (int c = 0; c < count; ++c) {
-                const float4 kk = w.sol.k[2 * s + c];
-                const float2 lam = w.sol.lam[2 * s + c];
+                const float4 kk = w.sol.k[SOL_AT(w, s, c)];
+                const float2 lam = w.sol.lam[SOL_AT(w, s, c)];
                 man.imp[2 * m + c] = make_float4(kk.y, lam.x, kk.z, lam.y);
             }
         }

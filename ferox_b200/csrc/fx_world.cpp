@@ -642,6 +642,12 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.inv_dt = 1.0f / dt;                                       // src/world.c:242
     d.solver_mode = w->solver_mode;
     {
+        // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
+        const bool contact_major = w->manifold_hint >= 400000;
+        d.sol_stride = contact_major ? d.cap_manifolds : 1u;
+        d.sol_mult = contact_major ? 1u : 2u;
+    }
+    {
         static const int narrow = [] { const char *e = std::getenv("FEROX_NARROWPHASE"); return !e ? 0 : (std::strcmp(e, "group8") == 0 ? 1 : (std::strcmp(e, "lane") == 0 ? 2 : 0)); }();
         d.narrow_mode = narrow;
     }
