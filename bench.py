@@ -378,6 +378,29 @@ def run_b200(args):
     e2e_copy_s, _ = e2e_loop(True)
     fb.check_error(L)
 
+    # ---- the same steps with a (no-op, compiled C) collision handler installed: every live manifold goes to the
+    # host before and after the solve and comes back (SURVEY.md section 8d asks for this second number) ----
+    handler_ms = None
+    noop_path = os.path.join(ROOT, "ferox_b200", "_build", "libfx_noop_handler.so")
+    if not strips and rank == 0 and os.path.exists(noop_path):
+        from ferox_b200 import capi
+        noop = C.CDLL(noop_path)
+        fn = C.cast(noop.fx_noop_collision_event, capi.CollisionEventFunc)
+        L.frSetWorldCollisionHandler(sc.world, capi.CollisionHandler(fn, fn))
+        hsteps = max(3, min(20, args.steps))
+        L.frStepWorld(sc.world, dt)
+        L.frxSynchronizeWorld(sc.world)
+        t0 = time.perf_counter()
+        for _ in range(hsteps):
+            L.frStepWorld(sc.world, dt)
+        L.frxSynchronizeWorld(sc.world)
+        handler_ms = (time.perf_counter() - t0) * 1e3 / hsteps
+        noop.fx_noop_collision_event_calls.restype = C.c_ulonglong
+        handler_calls = int(noop.fx_noop_collision_event_calls())
+        null = capi.CollisionEventFunc()
+        L.frSetWorldCollisionHandler(sc.world, capi.CollisionHandler(null, null))
+        fb.check_error(L)
+
     # ---- max over ranks ----
     if dist is not None:
         import torch
@@ -440,6 +463,9 @@ def run_b200(args):
                     "api": "frxApplyForces + frStepWorld (frxStripStep on a strip) + frxViewBodyStates (states land in the library's pinned host mirror)",
                     "value_copy_out": total_bodies * e2e_steps / e2e_copy_s,
                     "api_copy_out": "same with frxGetBodyStates (re-laid out into 6 caller-owned pageable arrays)"},
+            "handler_bridge": None if handler_ms is None else {
+                "ms_per_step": handler_ms, "value": n / (handler_ms * 1e-3), "unit": UNIT,
+                "note": "rank 0, wall clock, no-op C pre+post handlers installed: %d callbacks over the sample" % handler_calls},
             "gpu_launches": int(launches),
             "clocks": clocks,
         }

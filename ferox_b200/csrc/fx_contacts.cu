@@ -315,10 +315,20 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
                 Manifold m;
                 collide_circles(w.shapes[si.x].radius, load_xf(w, pr[j].x), w.shapes[sj.x].radius, load_xf(w, pr[j].y), m);
                 if (m.count) slot_store(slot[local], m);
-            } else if (si.y == FX_SHAPE_POLYGON && sj.y == FX_SHAPE_POLYGON) {
-                list_pp[atomicAdd(&s_npp, 1u)] = (unsigned short) local;
-            } else if ((si.y == FX_SHAPE_CIRCLE && sj.y == FX_SHAPE_POLYGON) || (si.y == FX_SHAPE_POLYGON && sj.y == FX_SHAPE_CIRCLE)) {
-                list_cp[atomicAdd(&s_ncp, 1u)] = (unsigned short) local;
+            } else {
+                // Two shapes whose bounding circles are apart have a separating axis: the reference's SAT / circle
+                // tests return "no collision" for them (src/collision.c:340-348,465-469), so this candidate is a miss
+                // without running them.  The reference has no such test (it goes from shared cells straight to
+                // SAT, App. A.2) and at cell = 2 body diameters most polygon candidates are this far apart.
+                const float4 pi4 = w.posrot[pr[j].x], pj4 = w.posrot[pr[j].y];
+                const float dx = pj4.x - pi4.x, dy = pj4.y - pi4.y;
+                const float reach = w.shapes[si.x].bound + w.shapes[sj.x].bound;
+                if (dx * dx + dy * dy > reach * reach * 1.0001f) continue;      // NaN compares false: falls through
+                if (si.y == FX_SHAPE_POLYGON && sj.y == FX_SHAPE_POLYGON) {
+                    list_pp[atomicAdd(&s_npp, 1u)] = (unsigned short) local;
+                } else if ((si.y == FX_SHAPE_CIRCLE && sj.y == FX_SHAPE_POLYGON) || (si.y == FX_SHAPE_POLYGON && sj.y == FX_SHAPE_CIRCLE)) {
+                    list_cp[atomicAdd(&s_ncp, 1u)] = (unsigned short) local;
+                }
             }
         }
         __syncthreads();

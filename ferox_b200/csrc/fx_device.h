@@ -30,7 +30,7 @@ enum { FX_BODY_UNKNOWN = 0, FX_BODY_STATIC = 1, FX_BODY_KINEMATIC = 2, FX_BODY_D
 struct __align__(16) ShapeDev {
     int type, nv;
     float radius, friction;
-    float restitution, pad0, pad1, pad2;
+    float restitution, bound, pad1, pad2;   // bound: radius of a circle around the body position that holds the shape (slightly inflated)
     V2 verts[FX_MAX_VERTS];
     V2 normals[FX_MAX_VERTS];
 };

@@ -407,10 +407,16 @@ static void fill_shape_dev(ShapeDev &d, const frShape *s) {
     d.radius = s->radius;
     d.friction = s->material.friction;
     d.restitution = s->material.restitution;
+    float far2 = 0.0f;
     for (int k = 0; k < d.nv && k < FX_MAX_VERTS; ++k) {
         d.verts[k] = v2(s->vertices.data[k].x, s->vertices.data[k].y);
         d.normals[k] = v2(s->normals.data[k].x, s->normals.data[k].y);
+        const float l2 = d.verts[k].x * d.verts[k].x + d.verts[k].y * d.verts[k].y;
+        if (l2 > far2) far2 = l2;
     }
+    // conservative bounding radius for the narrow phase's early miss (fx_contacts.cu): never smaller than the shape
+    const float reach = (s->type == FR_SHAPE_POLYGON) ? std::sqrt(far2) : std::fabs(s->radius);
+    d.bound = reach * 1.0001f + 1e-5f;
 }
 static int shape_slot(frWorld *w, frShape *s) {
     if (!s) return -1;
