@@ -34,7 +34,9 @@ extern long long g_fx_launches;
 
 namespace cg = cooperative_groups;
 
-#define SV_BLOCK 256
+#ifndef SV_BLOCK
+#define SV_BLOCK 512   // [measured] 65k bodies: 128 -> 0.359, 256 -> 0.339, 512 -> 0.330 ms per solve; no difference at 1 M
+#endif
 // per-contact solver records: slot-major [slot][2] for small worlds (the rare second contact of a slot shares the
 // sector of the first, so its load is an L1 hit inside a latency-bound phase) or CONTACT-MAJOR [2][slot] for
 // large ones (93 % of the manifolds of a pile carry one contact, Q/M = 1.07: side by side, every sweep dragged
@@ -145,7 +147,11 @@ __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, flo
 #define SV_SETUP 1
 #define SV_SWEEP 2
 #define SV_WRITEBACK 4
-__global__ void __launch_bounds__(SV_BLOCK) k_solve_colored(DevWorld w, int iterations, int phases) {
+// Two builds of the same kernel: MINB = 1 may use 128 registers (96 used, no spills; one block per SM: the
+// latency-bound small-world case), MINB = 2 is held to 64 registers so that two blocks fit an SM (large worlds
+// want the threads).  [measured] solve at 65k bodies 0.323 (MINB 1) vs 0.330 ms; at 1 M bodies 2.46 vs 2.27 ms.
+template <int MINB>
+__global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, int iterations, int phases) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_hist[FX_MAX_COLORS];
     __shared__ unsigned int s_off[FX_MAX_COLORS + 1];
@@ -659,18 +665,20 @@ __global__ void k_solve_serial(DevWorld w, SerialOrder o, int iterations) {
 int fx_query_coop_blocks(int device) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_colored, SV_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_colored<2>, SV_BLOCK, 0);
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
 }
+
+static bool solve_wide(long long work_hint) { return work_hint >= 400000; }
 
 int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint) {
     // A phase holds ~1/8 of the manifolds (one colour).  Fewer resident blocks make the ~100 grid
     // barriers of a solve cheaper, so take just enough blocks to give every manifold of a phase its
     // own thread, in whole multiples of the SM count, at least one block per SM.
     long long want = (work_hint / 6 + SV_BLOCK - 1) / SV_BLOCK;
-    int per_sm = cx.coop_blocks / (cx.num_sms > 0 ? cx.num_sms : 1);
+    int per_sm = solve_wide(work_hint) ? cx.coop_blocks / (cx.num_sms > 0 ? cx.num_sms : 1) : 1;
     long long k = (want + cx.num_sms - 1) / cx.num_sms;
     if (k < 1) k = 1;
     if (k > per_sm) k = per_sm;
@@ -683,7 +691,8 @@ void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int itera
     const int blocks = fx_solve_colored_blocks(cx, work_hint);
     DevWorld wc = w;
     void *args[] = { (void *) &wc, (void *) &iterations, (void *) &phases };
-    cudaLaunchCooperativeKernel((const void *) k_solve_colored, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);
+    const void *kernel = solve_wide(work_hint) ? (const void *) k_solve_colored<2> : (const void *) k_solve_colored<1>;
+    cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);
     ++g_fx_launches;
 }
 
