@@ -156,9 +156,9 @@ struct DevWorld {
     unsigned int *color_off;             // [FX_MAX_COLORS + 1]
     unsigned long long *body_mask;       // colours already used by each body
     unsigned long long *body_dup;        // colours seen more than once on a body (inherited clashes)
-    unsigned int *winner;                // colouring: per-body claim
+    unsigned int *winner;                // colouring: per-body claim, [2][n] (alternating by round)
     int2 *cbody;                         // per manifold: the bodies that constrain its colour (-1: none)
-    unsigned int *color_scratch;         // [3][FX_MAX_COLORS]: counts, fill cursors, per-round remaining
+    unsigned int *color_scratch;         // [4][FX_MAX_COLORS]: counts, fill cursors, per-round remaining, flags
     // single-pass ordered compaction (decoupled look-back)
     StepCountersDev *ctr;                // current step
     unsigned int *prev_count;            // number of entries in the prev manifold set

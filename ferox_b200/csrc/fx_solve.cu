@@ -171,12 +171,14 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     // with the colour they had (carried through the contact cache); those colours are re-validated
     // here (a body that became dynamic may now see one colour twice) and only new manifolds go
     // through the greedy rounds below.
+    unsigned int *const dup_flag = w.color_scratch + 3 * FX_MAX_COLORS;
     for (unsigned int i = tid; i < (unsigned int) w.n; i += nth) {
         w.body_mask[i] = 0ull;
         w.body_dup[i] = 0ull;
         w.winner[i] = 0xffffffffu;
+        w.winner[(size_t) w.n + i] = 0xffffffffu;
     }
-    for (unsigned int i = tid; i < 3 * FX_MAX_COLORS; i += nth) w.color_scratch[i] = 0u;
+    for (unsigned int i = tid; i < 4 * FX_MAX_COLORS; i += nth) w.color_scratch[i] = 0u;
     grid.sync();
     for (unsigned int m = tid; m < M; m += nth) {
         int2 b = man.body[m];
@@ -185,41 +187,57 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
         const int col = man.meta[m].y;
         if (col >= 0) {
             const unsigned long long bit = 1ull << col;
-            if (cb.x >= 0 && (atomicOr(&w.body_mask[cb.x], bit) & bit)) atomicOr(&w.body_dup[cb.x], bit);
-            if (cb.y >= 0 && (atomicOr(&w.body_mask[cb.y], bit) & bit)) atomicOr(&w.body_dup[cb.y], bit);
+            bool clash = false;
+            if (cb.x >= 0 && (atomicOr(&w.body_mask[cb.x], bit) & bit)) { atomicOr(&w.body_dup[cb.x], bit); clash = true; }
+            if (cb.y >= 0 && (atomicOr(&w.body_mask[cb.y], bit) & bit)) { atomicOr(&w.body_dup[cb.y], bit); clash = true; }
+            if (clash) *dup_flag = 1u;
         }
     }
     grid.sync();
-    for (unsigned int m = tid; m < M; m += nth) {
-        int2 meta = man.meta[m];
-        if (meta.y < 0) continue;
-        const unsigned long long bit = 1ull << meta.y;
-        const int2 cb = w.cbody[m];
-        if ((cb.x >= 0 && (w.body_dup[cb.x] & bit)) || (cb.y >= 0 && (w.body_dup[cb.y] & bit))) {
-            meta.y = -1;                              // every manifold of a clash is recoloured
-            man.meta[m] = meta;
-        }
-    }
-    grid.sync();
-
-    // ---- phase 1: colouring rounds
-    for (unsigned int round = 0; round < 64u; ++round) {
+    if (*reinterpret_cast<volatile unsigned int *>(dup_flag)) {     // rare (a body changed type or flags): grid-uniform
         for (unsigned int m = tid; m < M; m += nth) {
-            if (man.meta[m].y >= 0) continue;
-            int2 cb = w.cbody[m];
-            unsigned int tk = ticket_of(m, round);
-            if (cb.x >= 0) atomicMin(&w.winner[cb.x], tk);
-            if (cb.y >= 0) atomicMin(&w.winner[cb.y], tk);
+            int2 meta = man.meta[m];
+            if (meta.y < 0) continue;
+            const unsigned long long bit = 1ull << meta.y;
+            const int2 cb = w.cbody[m];
+            if ((cb.x >= 0 && (w.body_dup[cb.x] & bit)) || (cb.y >= 0 && (w.body_dup[cb.y] & bit))) {
+                meta.y = -1;                              // every manifold of a clash is recoloured
+                man.meta[m] = meta;
+            }
         }
         grid.sync();
+    }
+
+    // ---- phase 1: colouring rounds (Luby style: a manifold takes the lowest free colour when its ticket is the
+    // smallest on both of its bodies).  One grid barrier per round: the claims of round r+1 go to the other half of
+    // `winner` while stragglers may still read the claims of round r; tickets shrink from round to round, so a
+    // half needs no reset when it is reused two rounds later.
+    for (unsigned int m = tid; m < M; m += nth) {
+        if (man.meta[m].y >= 0) continue;
+        const int2 cb = w.cbody[m];
+        const unsigned int tk = ticket_of(m, 0u);
+        if (cb.x >= 0) atomicMin(&w.winner[cb.x], tk);
+        if (cb.y >= 0) atomicMin(&w.winner[cb.y], tk);
+    }
+    for (unsigned int round = 0; round <= 64u; ++round) {
+        grid.sync();
+        if (round > 0u && (color_rem[round - 1u] == 0u || round == 64u)) { if (tid == 0) w.ctr->uncolored = round; break; }
+        const unsigned int *win = w.winner + (size_t) (round & 1u) * (size_t) w.n;
+        unsigned int *next = w.winner + (size_t) ((round + 1u) & 1u) * (size_t) w.n;
         unsigned int left = 0u;
         for (unsigned int m = tid; m < M; m += nth) {
             int2 meta = man.meta[m];
             if (meta.y >= 0) continue;
-            int2 cb = w.cbody[m];
-            unsigned int tk = ticket_of(m, round);
-            bool won = (cb.x < 0 || w.winner[cb.x] == tk) && (cb.y < 0 || w.winner[cb.y] == tk);
-            if (!won) { ++left; continue; }
+            const int2 cb = w.cbody[m];
+            const unsigned int tk = ticket_of(m, round);
+            const bool won = (cb.x < 0 || win[cb.x] == tk) && (cb.y < 0 || win[cb.y] == tk);
+            if (!won) {
+                ++left;
+                const unsigned int tn = ticket_of(m, round + 1u);        // claim for the next round
+                if (cb.x >= 0) atomicMin(&next[cb.x], tn);
+                if (cb.y >= 0) atomicMin(&next[cb.y], tn);
+                continue;
+            }
             unsigned long long used = (cb.x >= 0 ? w.body_mask[cb.x] : 0ull) | (cb.y >= 0 ? w.body_mask[cb.y] : 0ull);
             int col = __ffsll((long long) ~used) - 1;
             if (col < 0) { col = FX_MAX_COLORS - 1; atomicOr(&w.ctr->overflow, 8u); }
@@ -229,8 +247,6 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
             if (cb.y >= 0) w.body_mask[cb.y] |= (1ull << col);
         }
         if (left) atomicAdd(&color_rem[round], left);
-        grid.sync();
-        if (color_rem[round] == 0u) { if (tid == 0) w.ctr->uncolored = round + 1u; break; }
     }
 
     // ---- phase 2: counting sort of manifold indices by colour

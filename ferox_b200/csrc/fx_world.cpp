@@ -117,7 +117,7 @@ static bool world_device_init(frWorld *w) {
     fx_cuda_ok(cudaMalloc((void **) &w->dw.prev_count, sizeof(unsigned int)), "cudaMalloc");
     fx_cuda_ok(cudaMalloc((void **) &w->dw.cur_flip, sizeof(int)), "cudaMalloc");
     fx_cuda_ok(cudaMalloc((void **) &w->dw.color_off, (FX_MAX_COLORS + 1) * sizeof(unsigned int)), "cudaMalloc");
-    fx_cuda_ok(cudaMalloc((void **) &w->dw.color_scratch, 3 * FX_MAX_COLORS * sizeof(unsigned int)), "cudaMalloc");
+    fx_cuda_ok(cudaMalloc((void **) &w->dw.color_scratch, 4 * FX_MAX_COLORS * sizeof(unsigned int)), "cudaMalloc");
     cudaMemsetAsync(w->dw.ctr, 0, sizeof(StepCountersDev), w->stream);
     cudaMemsetAsync(w->dw.prev_count, 0, sizeof(unsigned int), w->stream);
     cudaMemsetAsync(w->dw.cur_flip, 0, sizeof(int), w->stream);
@@ -289,7 +289,7 @@ static bool ensure_body_capacity(frWorld *w, int need) {
          dev_realloc(d.shape, o, n, s, true) && dev_realloc(d.uid, o, n, s, true) && dev_realloc(w->d_group, o, n, s, true) &&
          dev_realloc(d.cell_cnt, 0, n, s, false) && dev_realloc(d.cell_off, 0, n, s, false) &&
          dev_realloc(d.large_list, 0, n, s, false) && dev_realloc(d.body_mask, 0, n, s, false) && dev_realloc(d.body_dup, 0, n, s, false) &&
-         dev_realloc(d.winner, 0, n, s, false);
+         dev_realloc(d.winner, 0, 2 * (size_t) n, s, false);
     d.cap_large = (unsigned int) n;
     w->body_cap = cap;
     // the look-back status words of the per-body sweep are sized by the body capacity
