@@ -190,6 +190,7 @@ static void world_free_device(frWorld *w) {
 
 static void detach_body(frWorld *w, frBody *b);
 
+void fx_release_manifold_host(frWorld *w);
 extern "C" void frReleaseWorld(frWorld *w) {
     if (!w) return;
     if (w->device_ok) { cudaSetDevice(w->device); fx_world_pull(w); }
@@ -197,6 +198,7 @@ extern "C" void frReleaseWorld(frWorld *w) {
     for (frBody *b : w->bodies) std::free(b);
     w->bodies.clear();
     if (w->device_ok || w->stream) world_free_device(w);
+    fx_release_manifold_host(w);
     delete w;
 }
 
@@ -730,6 +732,7 @@ static void grow_if_crowded(frWorld *w) {
 }
 
 static void run_handler(frWorld *w, frCollisionEventFunc fn);
+static void mh_mark_stale(frWorld *w);
 
 static void prof_mark(frWorld *w) {
     if (!w->profiling) return;
@@ -744,6 +747,7 @@ static void prof_mark(frWorld *w) {
 // the kernel / memset / memcpy sequence of one step on the world's stream (also what gets captured)
 static void launch_step_sequence(frWorld *w, bool collide, bool has_handler, bool serial, long long hint) {
     DevWorld &d = w->dw;
+    mh_mark_stale(w);
     prof_mark(w);
     fx_launch_begin_step(d, w->cx);
     if (serial && w->lex.zero_base) cudaMemsetAsync(w->lex.zero_base, 0, w->lex.zero_bytes, w->stream);
@@ -1276,15 +1280,48 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
 // ---------------------------------------------------------------------------------------------
 // manifold download / upload (introspection and the collision-handler bridge)
 // ---------------------------------------------------------------------------------------------
+// grow-only pinned host array (D2H into pageable std::vector storage ran at a few GB/s and paid a page-fault
+// storm per step: [measured] 15 ms per 65k-body step with a no-op handler installed)
+template <typename T>
+struct PinnedBuf {
+    T *p = nullptr;
+    size_t cap = 0, n = 0;
+    void resize(size_t k) {
+        if (k > cap) {
+            if (p) cudaFreeHost(p);
+            cap = k + k / 4 + 1024;
+            if (cudaMallocHost((void **) &p, cap * sizeof(T)) != cudaSuccess) { p = nullptr; cap = 0; k = 0; }
+        }
+        n = k;
+    }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+};
 struct ManifoldHost {
-    std::vector<uint2> key;
-    std::vector<int2> body, meta;
-    std::vector<float4> hdr, geo, imp;
-    std::vector<int> cid;
+    PinnedBuf<uint2> key;
+    PinnedBuf<int2> body, meta;
+    PinnedBuf<float4> hdr, geo, imp;
+    PinnedBuf<int> cid;
     std::vector<unsigned long long> order_keys;
+    std::vector<unsigned int> order;
     unsigned int count = 0;
     int set = 0;
+    bool fresh = false;          // holds this step's live set (only the impulses can have changed since)
 };
+static ManifoldHost &world_mh(frWorld *w) {
+    if (!w->mh_cache) w->mh_cache = new ManifoldHost();
+    return *static_cast<ManifoldHost *>(w->mh_cache);
+}
+static void mh_mark_stale(frWorld *w) {
+    if (w->mh_cache) static_cast<ManifoldHost *>(w->mh_cache)->fresh = false;
+}
+void fx_release_manifold_host(frWorld *w) {
+    delete static_cast<ManifoldHost *>(w->mh_cache);
+    w->mh_cache = nullptr;
+}
 
 // `after_finish`: the step has completed (cur_flip already toggled), so the live set is flip ^ 1
 static bool download_manifolds(frWorld *w, ManifoldHost &mh, bool after_finish) {
@@ -1297,6 +1334,11 @@ static bool download_manifolds(frWorld *w, ManifoldHost &mh, bool after_finish) 
     else cudaMemcpyAsync(&m, &d.ctr->n_manifolds, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
     if (!fx_cuda_ok(cudaStreamSynchronize(s), "manifold count")) return false;
     const int set = after_finish ? (flip ^ 1) : flip;
+    if (mh.fresh && mh.set == set && mh.count == m && m > 0) {
+        // second sweep of the same step (post-step handler): only the solver's impulses are new
+        cudaMemcpyAsync(mh.imp.data(), d.man[set].imp, 2 * (size_t) m * sizeof(float4), cudaMemcpyDeviceToHost, s);
+        return fx_cuda_ok(cudaStreamSynchronize(s), "manifold download");
+    }
     mh.set = set;
     mh.count = m;
     if (m == 0 || d.cap_manifolds == 0) { mh.count = 0; return true; }
@@ -1364,11 +1406,13 @@ static void visiting_order(const ManifoldHost &mh, std::vector<unsigned int> &or
 // collision-handler sweep (src/world.c:209-214 / :254-259): every entry with count > 0, in solver
 // order, on the caller's thread; the handler may edit *value and enqueue add/remove requests.
 static void run_handler(frWorld *w, frCollisionEventFunc fn) {
-    ManifoldHost mh;
+    ManifoldHost &mh = world_mh(w);
+    const bool second_sweep = mh.fresh;
     if (!download_manifolds(w, mh, false) || mh.count == 0) return;
     fx_world_pull(w);   // getters inside the handler must see current state
-    std::vector<unsigned int> order;
-    visiting_order(mh, order);
+    std::vector<unsigned int> &order = mh.order;
+    if (!second_sweep) visiting_order(mh, order);
+    mh.fresh = true;
     bool edited = false;
     for (unsigned int i : order) {
         if (mh.meta[i].x <= 0) continue;
@@ -1396,9 +1440,10 @@ static void run_handler(frWorld *w, frCollisionEventFunc fn) {
 extern "C" int frxGetManifolds(frWorld *w, frxManifold *out, int max) {
     if (!w || !w->device_ok) return 0;
     cudaSetDevice(w->device);
-    ManifoldHost mh;
+    ManifoldHost &mh = world_mh(w);
+    mh.fresh = false;
     if (!download_manifolds(w, mh, true)) return 0;
-    std::vector<unsigned int> order;
+    std::vector<unsigned int> &order = mh.order;
     visiting_order(mh, order);
     int n = 0;
     for (unsigned int i : order) {
