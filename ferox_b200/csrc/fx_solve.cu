@@ -25,6 +25,7 @@
 // reference src/external/stb_ds.h:1436-1448, 1506-1520) with the same per-contact arithmetic
 // (fx_solver.cuh), which makes a step bit-comparable with the CPU reference.
 #include <cooperative_groups.h>
+#include <cstdlib>
 
 #include "fx_device.h"
 #include "fx_kernels.h"
@@ -104,41 +105,55 @@ __device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const 
     vel[b.y - lo] = make_float4(vb.x, vb.y, vb.w, inv_mb);
 }
 
-__device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, float4 *vel, int lo) {
-    // level 1: everything addressed by the slot alone, issued together
-    const int cs = w.sol.count_src[s];
-    const int2 b = w.sol.body[s];
-    const float4 nt = w.sol.nt[s];
-    const float4 mat = w.sol.mat[s];
-    const float4 r0 = w.sol.r[SOL_AT(w, s, 0)], u0 = w.sol.u[SOL_AT(w, s, 0)], k0 = w.sol.k[SOL_AT(w, s, 0)];
-    float2 l0 = w.sol.lam[SOL_AT(w, s, 0)];
-    const int count = cs & 3;
+// what a sweep reads of a slot through the slot index alone ("level 1"); it does not depend on any velocity
+struct SweepRec {
+    int cs;
+    int2 b;
+    float4 nt, mat, r0, u0, k0;
+    float2 l0;
+};
+__device__ __forceinline__ SweepRec sweep_load(const DevWorld &w, unsigned int s) {
+    SweepRec q;
+    q.cs = w.sol.count_src[s];
+    q.b = w.sol.body[s];
+    q.nt = w.sol.nt[s];
+    q.mat = w.sol.mat[s];
+    q.r0 = w.sol.r[SOL_AT(w, s, 0)]; q.u0 = w.sol.u[SOL_AT(w, s, 0)]; q.k0 = w.sol.k[SOL_AT(w, s, 0)];
+    q.l0 = w.sol.lam[SOL_AT(w, s, 0)];
+    return q;
+}
+__device__ __forceinline__ void sweep_apply(const DevWorld &w, unsigned int s, SweepRec q, float4 *vel, int lo) {
+    const int count = q.cs & 3;
     if (count == 0) return;
     // level 2: the velocities (addressed through b) and, for the few two-contact manifolds, the second record
+    const int2 b = q.b;
     float4 va4 = vel[b.x - lo], vb4 = vel[b.y - lo];
-    float4 r1 = r0, u1 = u0, k1 = k0;
-    float2 l1 = l0;
+    float4 r1 = q.r0, u1 = q.u0, k1 = q.k0;
+    float2 l0 = q.l0, l1 = q.l0;
     if (count > 1) {
         r1 = w.sol.r[SOL_AT(w, s, 1)]; u1 = w.sol.u[SOL_AT(w, s, 1)]; k1 = w.sol.k[SOL_AT(w, s, 1)];
         l1 = w.sol.lam[SOL_AT(w, s, 1)];
     }
     Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
-    const V2 n = v2(nt.x, nt.y), t = v2(nt.z, nt.w);
+    const V2 n = v2(q.nt.x, q.nt.y), t = v2(q.nt.z, q.nt.w);
     ContactK k;
-    k.r1 = v2(r0.x, r0.y); k.r2 = v2(r0.z, r0.w);
-    k.u1 = v2(u0.x, u0.y); k.u2 = v2(u0.z, u0.w);
-    k.bias = k0.x; k.nmass = k0.y; k.tmass = k0.z;
-    contact_resolve(k, n, t, mat.x, mat.y, l0.x, l0.y, va4.w, vb4.w, mat.z, mat.w, va, vb);
+    k.r1 = v2(q.r0.x, q.r0.y); k.r2 = v2(q.r0.z, q.r0.w);
+    k.u1 = v2(q.u0.x, q.u0.y); k.u2 = v2(q.u0.z, q.u0.w);
+    k.bias = q.k0.x; k.nmass = q.k0.y; k.tmass = q.k0.z;
+    contact_resolve(k, n, t, q.mat.x, q.mat.y, l0.x, l0.y, va4.w, vb4.w, q.mat.z, q.mat.w, va, vb);
     if (count > 1) {
         k.r1 = v2(r1.x, r1.y); k.r2 = v2(r1.z, r1.w);
         k.u1 = v2(u1.x, u1.y); k.u2 = v2(u1.z, u1.w);
         k.bias = k1.x; k.nmass = k1.y; k.tmass = k1.z;
-        contact_resolve(k, n, t, mat.x, mat.y, l1.x, l1.y, va4.w, vb4.w, mat.z, mat.w, va, vb);
+        contact_resolve(k, n, t, q.mat.x, q.mat.y, l1.x, l1.y, va4.w, vb4.w, q.mat.z, q.mat.w, va, vb);
     }
     vel[b.x - lo] = make_float4(va.x, va.y, va.w, va4.w);
     vel[b.y - lo] = make_float4(vb.x, vb.y, vb.w, vb4.w);
     w.sol.lam[SOL_AT(w, s, 0)] = l0;
     if (count > 1) w.sol.lam[SOL_AT(w, s, 1)] = l1;
+}
+__device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, float4 *vel, int lo) {
+    sweep_apply(w, s, sweep_load(w, s), vel, lo);
 }
 
 // `phases`: bit 0 = colouring + ordering + solver records + warm start, bit 1 = `iterations` sweeps,
@@ -304,6 +319,8 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     }
     const unsigned int ncolors = s_ncolors;
     // ---- phase 4: Gauss-Seidel sweeps
+    // ([measured] fetching the next colour's records BEFORE the barrier -- software pipelining across grid.sync() --
+    // was bit-identical and slower: solve 0.313 -> 0.432 ms at 65k bodies; the barrier's fence waits for the loads)
     if (phases & SV_SWEEP)
     for (int it = 0; it < iterations; ++it)
         for (unsigned int c = 0; c < ncolors; ++c) {
@@ -687,7 +704,11 @@ int fx_query_coop_blocks(int device) {
     return sms * per_sm;
 }
 
-static bool solve_wide(long long work_hint) { return work_hint >= 400000; }
+static bool solve_wide(long long work_hint) {
+    // FEROX_SOLVE_WIDE=0|1 pins the variant (tests compare the two: they must agree bit for bit)
+    static const int pin = [] { const char *e = std::getenv("FEROX_SOLVE_WIDE"); return e ? std::atoi(e) : -1; }();
+    return pin >= 0 ? pin != 0 : work_hint >= 400000;
+}
 
 int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint) {
     // A phase holds ~1/8 of the manifolds (one colour).  Fewer resident blocks make the ~100 grid
@@ -699,6 +720,8 @@ int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint) {
     if (k < 1) k = 1;
     if (k > per_sm) k = per_sm;
     int blocks = (int) (k * cx.num_sms);
+    static const int force_blocks = [] { const char *e = std::getenv("FEROX_SOLVE_BLOCKS"); return e ? std::atoi(e) : 0; }();   // dev knob
+    if (force_blocks > 0 && force_blocks <= blocks) blocks = force_blocks;
     if (work_hint <= 2048) blocks = (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK) < 1 ? 1 : (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK);
     return blocks;
 }

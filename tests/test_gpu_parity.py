@@ -625,3 +625,27 @@ def test_state_views_equal_the_copying_getter(gpu):
         assert (p.x, p.y) == (float(v["posrot"][7, 0]), float(v["posrot"][7, 1]))
     fb.check_error(L)
     sc.release()
+
+
+def test_small_and_large_world_solver_builds_agree_bit_for_bit(gpu):
+    """k_solve_colored exists in two builds (fx_solve.cu): one block of up to 128 registers per SM for small
+    worlds, two blocks of 64 registers for large ones, with different grid sizes.  Same coloured order,
+    so the state after 200 steps must be identical; FEROX_SOLVE_WIDE pins the build, hence one
+    subprocess each."""
+    import hashlib, os, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import hashlib, numpy as np, ferox_b200 as fb\n"
+            "from ferox_b200 import scenes\n"
+            "L = fb.lib(); L.frxSetDevice(0)\n"
+            "sc = scenes.Scene(L, scenes.mixed_pile(6000, width=150.0), prime=False)\n"
+            "L.frStepWorld(sc.world, scenes.DT); L.frxStepWorldN(sc.world, scenes.DT, 200)\n"
+            "st = fb.body_states(L, sc.world); fb.check_error(L)\n"
+            "print('HASH', hashlib.sha1(b''.join(st[k].tobytes() for k in ('pos', 'angle', 'vel', 'omega'))).hexdigest(),"
+            " fb.step_counters(L, sc.world)['manifolds'])\n")
+    out = []
+    for wide in ("0", "1"):
+        env = dict(os.environ, FEROX_SOLVE_WIDE=wide, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][-1])
+    assert out[0] == out[1], out
