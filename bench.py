@@ -424,6 +424,16 @@ def run_b200(args):
         achieved = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
         step_bytes = (n * (160 + 2 * 24) + 104 * ctr["cellEntries"] + ctr["candidates"] * (64 + 92) + 1060 * M + 376 * Q)
         roof_kernel = "k_solve_colored"
+        traffic, traffic_src = None, None
+        if args.workload == "config2" and args.bodies == 65536:
+            # DRAM bytes of that kernel from the committed `ncu --set full` capture of this same command
+            cap = os.path.join(ROOT, "profiles", "r01_end_top_kernels_ncu.csv")
+            if os.path.exists(cap):
+                for row in open(cap):
+                    f = row.strip().split(",")
+                    if "k_solve_colored" in f[0]:
+                        traffic = (float(f[2]) + float(f[3])) * 1e6
+                        traffic_src = "profiles/r01_end_top_kernels_ncu.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
         if strips:
             # the strip step runs the solver as 12 separately launched stages with an exchange after each; there
             # are no per-stage events, so the roofline line is the WHOLE step of this rank's strip
@@ -456,7 +466,7 @@ def run_b200(args):
                                   enumerate(["broadphase", "narrowphase", "cache", "solve", "integrate"])},
             "step_algorithmic_GBps": step_bytes / (elapsed_ms / args.steps * 1e-3) / 1e9,
             "roofline": {"bound": "hbm", "kernel": roof_kernel, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "bytes_per_launch": solve_bytes, "ms_per_launch": solve_ms},
             "e2e": {"value": total_bodies * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 16),
                     "d2h_bytes_per_step": int(n * 52), "steps": e2e_steps, "checksum": checksum,
