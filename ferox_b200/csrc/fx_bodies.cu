@@ -82,6 +82,7 @@ __global__ void k_begin_step(DevWorld w) {
 
 __global__ void k_finish_step(DevWorld w, StepCountersDev *snapshot) {
     *w.prev_count = w.ctr->n_manifolds;
+    w.prev_count[1] = w.ctr->n_colors;              // the colouring squeezes its top colours next step (fx_solve.cu)
     *w.cur_flip ^= 1;
     *snapshot = *w.ctr;
 }

@@ -120,6 +120,7 @@ struct DevWorld {
     float timestamp;
     float dt, inv_dt;
     int solver_mode;
+    int color_squeeze;   // how many of last step's top colours are re-coloured every step (0: never)
     int narrow_mode;     // 0: one lane per pair (default), 1: 8 lanes per pair with shuffle arg-max over axes
     // bodies
     float4 *posrot, *vel, *mprop, *force, *aabb;
@@ -161,5 +162,5 @@ struct DevWorld {
     unsigned int *color_scratch;         // [4][FX_MAX_COLORS]: counts, fill cursors, per-round remaining, flags
     // single-pass ordered compaction (decoupled look-back)
     StepCountersDev *ctr;                // current step
-    unsigned int *prev_count;            // number of entries in the prev manifold set
+    unsigned int *prev_count;            // [0] number of entries in the prev manifold set, [1] colours used by the last solve
 };

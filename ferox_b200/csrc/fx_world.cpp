@@ -114,12 +114,12 @@ static bool world_device_init(frWorld *w) {
     std::memset(w->h_snapshot, 0, sizeof(StepCountersDev));
     fx_cuda_ok(cudaEventCreateWithFlags(&w->snapshot_ready, cudaEventDisableTiming), "cudaEventCreate");
     fx_cuda_ok(cudaMalloc((void **) &w->dw.ctr, sizeof(StepCountersDev)), "cudaMalloc");
-    fx_cuda_ok(cudaMalloc((void **) &w->dw.prev_count, sizeof(unsigned int)), "cudaMalloc");
+    fx_cuda_ok(cudaMalloc((void **) &w->dw.prev_count, 2 * sizeof(unsigned int)), "cudaMalloc");
     fx_cuda_ok(cudaMalloc((void **) &w->dw.cur_flip, sizeof(int)), "cudaMalloc");
     fx_cuda_ok(cudaMalloc((void **) &w->dw.color_off, (FX_MAX_COLORS + 1) * sizeof(unsigned int)), "cudaMalloc");
     fx_cuda_ok(cudaMalloc((void **) &w->dw.color_scratch, 4 * FX_MAX_COLORS * sizeof(unsigned int)), "cudaMalloc");
     cudaMemsetAsync(w->dw.ctr, 0, sizeof(StepCountersDev), w->stream);
-    cudaMemsetAsync(w->dw.prev_count, 0, sizeof(unsigned int), w->stream);
+    cudaMemsetAsync(w->dw.prev_count, 0, 2 * sizeof(unsigned int), w->stream);
     cudaMemsetAsync(w->dw.cur_flip, 0, sizeof(int), w->stream);
     w->device_ok = (g_error == 0) || true;
     return fx_cuda_ok(cudaStreamSynchronize(w->stream), "world init");
@@ -649,6 +649,7 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.dt = dt;
     d.inv_dt = 1.0f / dt;                                       // src/world.c:242
     d.solver_mode = w->solver_mode;
+    { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }
     {
         // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
         const bool contact_major = w->manifold_hint >= 400000;

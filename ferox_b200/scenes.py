@@ -184,7 +184,7 @@ def strip_pile_shapes(strip_width, height):
     return shapes
 
 
-def strip_pile(per_strip, k, n_strips, seed=1234, pitch=1.7, max_rows=96, storeys=1):
+def strip_pile(per_strip, k, n_strips, seed=1234, pitch=1.7, max_rows=96, storeys=1, circle_fraction=0.5):
     """Strip k of ONE pile of n_strips * per_strip dynamic bodies (50 % circles, 50 % regular 3..8-gons
     at random angles) resting on `storeys` floors stacked vertically, each pile at most `max_rows`
     lattice rows deep (see mixed_pile; several storeys keep an 8M-body world narrow enough for
@@ -207,7 +207,8 @@ def strip_pile(per_strip, k, n_strips, seed=1234, pitch=1.7, max_rows=96, storey
     row, col = j // per_row, j % per_row
     x = x0 + pitch * (col + 0.25 + 0.5 * (row & 1) * 0.5) + 0.05 * (u[:, 0] - 0.5)
     y = -1.0 - pitch * row - 0.05 * u[:, 1] - storey * storey_h
-    shape = np.where(u[:, 2] < 0.5, 2, 3 + np.minimum((u[:, 2] - 0.5) * 12.0, 5.0).astype(np.int64))
+    cf = float(circle_fraction)
+    shape = np.where(u[:, 2] < cf, 2, 3 + np.minimum((u[:, 2] - cf) * (6.0 / max(1e-9, 1.0 - cf)), 5.0).astype(np.int64))
     ang = u[:, 3] * 2.0 * math.pi
     types, shapes, pos, angle = [], [], [], []
     for f in range(storeys):
@@ -229,19 +230,21 @@ def strip_pile(per_strip, k, n_strips, seed=1234, pitch=1.7, max_rows=96, storey
 # --------------------------------------------------------------------------------------------------
 # config 3: granular column collapse, uniform circles (SURVEY.md section 8d "Config 3")
 # --------------------------------------------------------------------------------------------------
-def column_collapse(n=1048576, cols=512, seed=1, floor_width=16384.0, pitch=1.05, jitter=0.02):
+def column_collapse(n=1048576, cols=512, seed=1, floor_width=16384.0, pitch=1.05, jitter=0.02, friction=0.5, stagger=False,
+                    row_pitch=None):
     spec = SceneSpec(name="config3_column_collapse_%d" % n, cell=2.0)
     rows = (n + cols - 1) // cols
     spec.shapes = [
         ShapeSpec("rect", (floor_width, 2.0)),
         ShapeSpec("rect", (2.0, rows * pitch + 8.0)),
-        ShapeSpec("circle", (0.5,)),
+        ShapeSpec("circle", (0.5,), friction=friction),
     ]
     k = np.arange(n)
     row, col = k // cols, k % cols
     u = splitmix_uniform(seed, 2 * n)
-    x = 0.5 + pitch * col + jitter * (u[0::2] - 0.5)
-    y = -0.5 - pitch * row + jitter * (u[1::2] - 0.5) - 0.5 * jitter
+    rp = pitch if row_pitch is None else row_pitch
+    x = 0.5 + pitch * col + jitter * (u[0::2] - 0.5) + (0.5 * pitch * (row & 1) if stagger else 0.0)
+    y = -0.5 - rp * row + jitter * (u[1::2] - 0.5) - 0.5 * jitter
     pos = np.empty((n + 2, 2), np.float64)
     # floor top edge at y = 0, left wall right edge at x = 0; the right wall is "removed at t = 0"
     pos[0] = (floor_width * 0.5 - 64.0, 1.0)

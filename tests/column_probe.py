@@ -8,7 +8,12 @@ import bench
 L = fb.lib(); L.frxSetDevice(0)
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 1048576
 rows = int(sys.argv[2]) if len(sys.argv) > 2 else 96
-spec = scenes.column_collapse(n, cols=max(64, n // rows), pitch=1.2, jitter=0.2, floor_width=32768.0)
+if os.environ.get("STOREYS"):
+    spec, _, _ = scenes.strip_pile(n, 0, 1, storeys=int(os.environ["STOREYS"]), max_rows=rows, pitch=float(os.environ.get("PITCH", "1.2")), circle_fraction=1.0)
+else:
+    spec = scenes.column_collapse(n, cols=max(64, n // rows), pitch=float(os.environ.get('PITCH', '1.2')), jitter=float(os.environ.get('JIT', '0.2')), floor_width=32768.0,
+                                  friction=float(os.environ.get('FRIC', '0.5')), stagger=os.environ.get('STAG', '0') == '1',
+                                  row_pitch=float(os.environ['ROWP']) if 'ROWP' in os.environ else None)
 sc = bench.build_bulk_world(L, spec)
 L.frStepWorld(sc.world, scenes.DT)
 for k in range(14):
