@@ -106,3 +106,41 @@ def test_two_strips_on_two_gpus_over_nccl(gpu):
     assert abs(r["mean_y"] - r["mean_y_single"]) < 0.02 * abs(r["mean_y_single"]) + 0.05, r
     assert r["max_y"] < 0.6 and r["ke"] < 4.0 * r["ke_single"] + 1.0, r
     assert r["manifolds_single"] * 0.97 < r["manifolds"] < r["manifolds_single"] * 1.25, r
+
+
+def test_eight_strips_of_the_65k_pile_match_the_single_world_statistically(gpu):
+    """'parity shown by running the same code path at 65 k bodies on 2-8
+    strips vs 1 GPU'.  The BASELINE config-2 pile (65,536 mixed bodies, 1,160 units wide) cut into 8
+    strips, all on this GPU with in-process links, 400 steps."""
+    L = gpu
+    spec = scenes.mixed_pile(65536)
+    steps = 400
+    want, wc = undivided(L, spec, steps)
+    dyn = spec.body_type != capi.BODY_STATIC
+    width = float(spec.pos[dyn, 0].max() - spec.pos[dyn, 0].min())
+    x0 = float(spec.pos[dyn, 0].min())
+    cuts = [x0 + width * k / 8.0 for k in range(1, 8)]
+    ss = scenes.StripScene(L, spec, cuts=cuts, margin=5.0, ghost_cap=2048)
+    ss.step(1)
+    ss.step(steps)
+    fb.check_error(L)
+    got = ss.gather_states()
+    ctrs = [fb.step_counters(L, w) for w in ss.worlds]
+    assert all(c["overflow"] == 0 for c in ctrs)
+    assert np.isfinite(got["pos"][dyn]).all()
+    my, wy = got["pos"][dyn, 1].mean(), want["pos"][dyn, 1].mean()
+    assert abs(my - wy) < 0.01 * abs(wy) + 0.05, (my, wy)
+    assert got["pos"][dyn, 1].max() < 0.6
+    ke_s = (got["vel"][dyn] ** 2).sum(1).mean()
+    ke_w = (want["vel"][dyn] ** 2).sum(1).mean()
+    assert ke_s < 2.0 * ke_w + 0.5, (ke_s, ke_w)
+    m = sum(c["manifolds"] for c in ctrs)
+    assert wc["manifolds"] * 0.97 < m < wc["manifolds"] * 1.1, (m, wc["manifolds"])
+    # no hot spot at any cut: kinetic energy of the bodies within 10 units of a cut vs the rest
+    x = got["pos"][dyn, 0]
+    near = np.zeros(x.shape, bool)
+    for c in cuts:
+        near |= np.abs(x - c) < 10.0
+    v2 = (got["vel"][dyn] ** 2).sum(1)
+    assert v2[near].mean() < 3.0 * v2[~near].mean() + 0.5, (v2[near].mean(), v2[~near].mean())
+    ss.release()
