@@ -355,7 +355,12 @@ def run_b200(args):
     st = fb.body_states(L, sc.world)
     e2e_steps = max(10, min(args.steps, 100))
     f32p = C.POINTER(C.c_float)
-    vp, va, vv, vb = f32p(), f32p(), f32p(), f32p()
+    vp, va, vv, vb, fmap = f32p(), f32p(), f32p(), f32p(), f32p()
+    L.frxViewBodyStates(sc.world, C.byref(vp), C.byref(va), C.byref(vv), C.byref(vb))
+    inv_mass = np.ctypeslib.as_array(vv, shape=(n, 4))[:, 3].copy()
+    force4 = np.zeros((n, 4), np.float32)                                  # (fx, fy, torque, 0) per body
+    force4[:, :2] = force * (inv_mass > 0)[:, None]                        # frApplyForceToBody ignores immovable bodies
+    fview = [None, None]
 
     def e2e_loop(copy_out):
         """per step: forces from a host array (H2D), one step, every body state back in host memory (D2H)."""
@@ -363,7 +368,14 @@ def run_b200(args):
         t0 = time.perf_counter()
         acc = 0.0
         for _ in range(e2e_steps):
-            L.frxApplyForces(sc.world, ptr(force), None, n)            # host -> pinned mirror, H2D in the step
+            if copy_out:
+                L.frxApplyForces(sc.world, ptr(force), None, n)        # caller array -> pinned mirror, H2D in the step
+            else:
+                L.frxMapBodyForces(sc.world, C.byref(fmap))            # the caller accumulates in the pinned mirror itself
+                addr = C.cast(fmap, C.c_void_p).value
+                if addr != fview[0]:
+                    fview[0], fview[1] = addr, np.ctypeslib.as_array(fmap, shape=(n, 4))
+                np.add(fview[1], force4, out=fview[1])
             if strips:
                 sc.step(1)
             else:
@@ -476,9 +488,9 @@ def run_b200(args):
                          "bytes_per_launch": solve_bytes, "ms_per_launch": solve_ms},
             "e2e": {"value": total_bodies * e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(n * 16),
                     "d2h_bytes_per_step": int(n * 52), "steps": e2e_steps, "checksum": checksum,
-                    "api": "frxApplyForces + frStepWorld (frxStripStep on a strip) + frxViewBodyStates (states land in the library's pinned host mirror)",
+                    "api": "frxMapBodyForces + frStepWorld (frxStripStep on a strip) + frxViewBodyStates (forces written into, states read from the library's pinned host mirror)",
                     "value_copy_out": total_bodies * e2e_steps / e2e_copy_s,
-                    "api_copy_out": "same with frxGetBodyStates (re-laid out into 6 caller-owned pageable arrays)"},
+                    "api_copy_out": "frxApplyForces + step + frxGetBodyStates (caller-owned pageable arrays in, 6 caller-owned arrays out)"},
             "handler_bridge": None if handler_ms is None else {
                 "ms_per_step": handler_ms, "value": n / (handler_ms * 1e-3), "unit": UNIT,
                 "note": "rank 0, wall clock, no-op C pre+post handlers installed: %d callbacks over the sample" % handler_calls},

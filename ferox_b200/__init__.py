@@ -61,6 +61,7 @@ EXT_PROTOTYPES = {
     "frxGetStepCounters": (None, [P, C.POINTER(StepCounters)]),
     "frxGetBodyStates": (I, [P, P, P, P, P, P, P]),
     "frxViewBodyStates": (I, [P, P, P, P, P]),
+    "frxMapBodyForces": (I, [P, P]),
     "frxApplyForces": (I, [P, P, P, I]),
     "frxSetBodyVelocities": (I, [P, P, P, I]),
     "frxCreateBodies": (I, [P, I, i32p, i32p, P, f32p, P, P]),

@@ -1512,6 +1512,15 @@ extern "C" int frxViewBodyStates(frWorld *w, const float **posRot, const float *
     return (int) w->bodies.size();
 }
 
+extern "C" int frxMapBodyForces(frWorld *w, float **force) {
+    if (!w || !force) return 0;
+    if (w->device_ok) cudaSetDevice(w->device);
+    fx_world_pull(w);                      // also clears the mirror's accumulators if a step has run since
+    *force = reinterpret_cast<float *>(w->h.force);
+    w->dirty |= FX_DIRTY_FORCE;
+    return (int) w->bodies.size();
+}
+
 extern "C" int frxApplyForces(frWorld *w, const float *force, const float *torque, int n) {
     if (!w) return 0;
     fx_world_pull(w);

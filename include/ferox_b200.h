@@ -268,6 +268,11 @@ int frxGetBodyStates(frWorld *w, float *position, float *angle, float *sincos, f
    posRot float[n][4] = (x, y, sin, cos), angle float[n], velocity float[n][4] = (vx, vy, omega,
    1/mass), aabb float[n][4] = (x, y, w, h).  This is what the per-body getters read.  Returns n. */
 int frxViewBodyStates(frWorld *w, const float **posRot, const float **angle, const float **velocity, const float **aabb);
+/* Writable view of the force accumulators in the pinned host mirror: force float[n][4] = (fx, fy, torque, 0),
+   zero after every step (src/world.c:481-482); whatever the caller ADDS here before the next step is uploaded
+   with it, exactly as frApplyForceToBody would have accumulated it (the caller skips bodies that cannot move:
+   velocity[i][3], the inverse mass, is 0 for them).  Returns n. */
+int frxMapBodyForces(frWorld *w, float **force);
 /* adds force/torque to every body with inverse mass > 0, like n frApplyForceToBody calls at the
    body's centre plus a pure torque (src/rigid_body.c:299-306) */
 int frxApplyForces(frWorld *w, const float *force, const float *torque, int n);

@@ -649,3 +649,35 @@ def test_small_and_large_world_solver_builds_agree_bit_for_bit(gpu):
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][-1])
     assert out[0] == out[1], out
+
+
+def test_mapped_forces_equal_apply_force_calls(gpu):
+    """frxMapBodyForces hands out the pinned accumulators themselves: adding (fx, fy, torque) there must
+    move the world exactly like frxApplyForces / frApplyForceToBody, and the view reads zero again
+    after the step."""
+    import ctypes as C
+    L = gpu
+    out = []
+    for mapped in (False, True):
+        spec = scenes.mixed_pile(1500, width=60.0)
+        sc = scenes.Scene(L, spec, prime=False)
+        L.frStepWorld(sc.world, DT)
+        n = L.frGetBodyCountInWorld(sc.world)
+        f = np.zeros((n, 2), np.float32); f[:, 0] = 0.3; f[::3, 1] = -0.2
+        tq = np.linspace(-0.1, 0.1, n).astype(np.float32)
+        for _ in range(30):
+            if mapped:
+                p = C.POINTER(C.c_float)()
+                assert L.frxMapBodyForces(sc.world, C.byref(p)) == n
+                fv = np.ctypeslib.as_array(p, shape=(n, 4))
+                assert not fv.any()
+                movable = fb.body_state_views(L, sc.world)["vel"][:, 3] > 0
+                fv[movable, 0] += f[movable, 0]; fv[movable, 1] += f[movable, 1]; fv[movable, 2] += tq[movable]
+            else:
+                L.frxApplyForces(sc.world, f.ctypes.data_as(C.c_void_p), tq.ctypes.data_as(C.c_void_p), n)
+            L.frStepWorld(sc.world, DT)
+        fb.check_error(L)
+        out.append(fb.body_states(L, sc.world))
+        sc.release()
+    for k in ("pos", "angle", "vel", "omega"):
+        assert np.array_equal(out[0][k].view(np.uint32), out[1][k].view(np.uint32)), k
