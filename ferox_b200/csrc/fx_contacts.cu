@@ -429,9 +429,14 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
 
 // stale entries of the previous array that no candidate probed survive (App. A.7) unless the
 // timestamp rule (src/world.c:229-233) or a departed body removes them
+// Tiles of NP_BLOCK x CO_ITEMS entries: almost every entry of a settled pile was probed this step, so the work per
+// tile is tiny and the kernel is bound by the length of the look-back chain ([measured] 1 M bodies, 128-entry
+// tiles: 140 us for 3.7 MB of traffic).
+template <int CO_ITEMS>
 __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned long long *status, unsigned int *ticket) {
     const unsigned int nprev = *w.prev_count;
-    const unsigned int ntiles = (nprev + NP_BLOCK - 1) / NP_BLOCK;
+    const unsigned int tile_size = NP_BLOCK * CO_ITEMS;
+    const unsigned int ntiles = (nprev + tile_size - 1) / tile_size;
     const int cs = *w.cur_flip;
     const ManifoldSet cur = w.man[cs], prev = w.man[cs ^ 1];
     const unsigned int nhits = w.ctr->n_hits;
@@ -439,31 +444,37 @@ __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned lo
     for (;;) {
         unsigned int tile = claim_tile(ticket);
         if (tile >= ntiles) return;
-        const unsigned int p = tile * NP_BLOCK + threadIdx.x;
-        bool keep = false;
-        int2 body = make_int2(-1, -1);
-        int count = 0, color = -1;
-        if (p < nprev && !w.touched[p]) {
-            uint2 k = prev.key[p];
-            body.x = w.idx_of_uid[k.x];
-            body.y = w.idx_of_uid[k.y];
-            const int2 pm = prev.meta[p];
-            count = pm.x;
-            color = pm.y;
-            keep = body.x >= 0 && body.y >= 0;
-            for (int c = 0; c < count && keep; ++c)
-                if (w.timestamp - prev.geo[2 * p + c].w > w.dt) keep = false;
+        const unsigned int first = tile * tile_size + threadIdx.x * CO_ITEMS;
+        unsigned int keep_mask = 0u, kept = 0u, q = 0u;
+        int2 body[CO_ITEMS];
+#pragma unroll
+        for (int j = 0; j < CO_ITEMS; ++j) {
+            const unsigned int p = first + j;
+            body[j] = make_int2(-1, -1);
+            if (p < nprev && !w.touched[p]) {
+                uint2 k = prev.key[p];
+                body[j].x = w.idx_of_uid[k.x];
+                body[j].y = w.idx_of_uid[k.y];
+                const int count = prev.meta[p].x;
+                bool keep = body[j].x >= 0 && body[j].y >= 0;
+                for (int c = 0; c < count && keep; ++c)
+                    if (w.timestamp - prev.geo[2 * p + c].w > w.dt) keep = false;
+                if (keep) { keep_mask |= 1u << j; ++kept; q += (unsigned int) count; }
+            }
         }
         unsigned int total;
-        unsigned int excl = block_exclusive_scan<NP_BLOCK>(keep ? 1u : 0u, &total);
+        unsigned int excl = block_exclusive_scan<NP_BLOCK>(kept, &total);
         unsigned int base = tile_exclusive_prefix(status, tile, total);
-        if (keep) {
-            unsigned int pos = nhits + base + excl;
+        unsigned int pos = nhits + base + excl;
+#pragma unroll
+        for (int j = 0; j < CO_ITEMS; ++j) {
+            if (!(keep_mask & (1u << j))) continue;
+            const unsigned int p = first + j;
             if (pos < w.cap_manifolds) {
                 cur.key[pos] = prev.key[p];
-                cur.body[pos] = body;
+                cur.body[pos] = body[j];
                 cur.hdr[pos] = prev.hdr[p];
-                cur.meta[pos] = make_int2(count, color);
+                cur.meta[pos] = prev.meta[p];
                 cur.geo[2 * pos] = prev.geo[2 * p];
                 cur.geo[2 * pos + 1] = prev.geo[2 * p + 1];
                 cur.imp[2 * pos] = prev.imp[2 * p];
@@ -471,8 +482,8 @@ __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned lo
                 cur.cid[2 * pos] = prev.cid[2 * p];
                 cur.cid[2 * pos + 1] = prev.cid[2 * p + 1];
             }
+            ++pos;
         }
-        unsigned int q = keep ? (unsigned int) count : 0u;
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);
         if (lane_id() == 0 && q) atomicAdd(&w.ctr->n_contacts, q);
@@ -545,7 +556,11 @@ void fx_launch_narrowphase(const DevWorld &w, const FxLaunchCtx &cx) {
 
 void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx) {
     cudaStream_t s = cx.stream;
-    k_carry_over<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7); ++g_fx_launches;
+    // large worlds (the host's contact-major switch, fill_dev_params): 1,024-entry tiles shorten the look-back chain;
+    // small ones keep one entry per thread ([measured] 65k bodies: 8 entries per thread cost +6 us)
+    if (w.sol_mult == 1u) k_carry_over<8><<<grid_for((long long) w.cap_manifolds, NP_BLOCK * 8, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7);
+    else k_carry_over<1><<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7);
+    ++g_fx_launches;
     cudaMemsetAsync(w.h_key, 0xff, (size_t) w.cap_hash * sizeof(unsigned long long), s);
     k_hash_build<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w); ++g_fx_launches;
 }
