@@ -30,16 +30,31 @@ __device__ __forceinline__ unsigned int hash_slot(unsigned long long key, unsign
     return (unsigned int) (z >> 32) & mask;
 }
 
-__device__ __forceinline__ int hash_find(const DevWorld &w, unsigned long long key) {
+// `keys`: the key column of the dense array the table was built over (the previous set while the narrow phase runs)
+__device__ __forceinline__ int hash_find(const DevWorld &w, unsigned long long key, const uint2 *keys) {
     const unsigned int mask = w.cap_hash - 1u;
     unsigned int s = hash_slot(key, mask);
     for (unsigned int probes = 0; probes < w.cap_hash; ++probes) {
-        unsigned long long k = w.h_key[s];
-        if (k == key) return (int) w.h_val[s];
-        if (k == HASH_EMPTY) return -1;
+        const unsigned int v = w.h_slot[s];
+        if (v == 0xffffffffu) return -1;
+        const uint2 k = keys[v];
+        if ((((unsigned long long) k.x << 32) | (unsigned long long) k.y) == key) return (int) v;
         s = (s + 1u) & mask;
     }
     return -1;
+}
+__device__ __forceinline__ void hash_insert(const DevWorld &w, const uint2 *keys, unsigned int i) {
+    const unsigned int mask = w.cap_hash - 1u;
+    const uint2 k = keys[i];
+    const unsigned long long key = ((unsigned long long) k.x << 32) | (unsigned long long) k.y;
+    unsigned int s = hash_slot(key, mask);
+    for (unsigned int probes = 0; probes < w.cap_hash; ++probes) {
+        const unsigned int v = atomicCAS(&w.h_slot[s], 0xffffffffu, i);
+        if (v == 0xffffffffu) return;
+        const uint2 o = keys[v];
+        if (o.x == k.x && o.y == k.y) return;            // the pair is already indexed (cannot happen: keys are unique)
+        s = (s + 1u) & mask;
+    }
 }
 
 __device__ __forceinline__ Xf load_xf(const DevWorld &w, int i) {
@@ -193,7 +208,7 @@ __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned l
         int color = -1;
         if (valid) {
             key = ((unsigned long long) w.uid[pr.x] << 32) | (unsigned long long) w.uid[pr.y];
-            old = hash_find(w, key);
+            old = hash_find(w, key, prev.key);
             if (old >= 0) w.touched[old] = 1;
             w.cand_hit[c] = hit ? 1 : 0;
         }
@@ -375,7 +390,7 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
             const bool hit = sl.count > 0;
             const unsigned int ua = w.uid[pr[j].x], ub = w.uid[pr[j].y];
             const unsigned long long key = ((unsigned long long) ua << 32) | (unsigned long long) ub;
-            const int old = hash_find(w, key);                      // src/world.c:347-394
+            const int old = hash_find(w, key, prev.key);            // src/world.c:347-394
             if (old >= 0) w.touched[old] = 1;
             w.cand_hit[c] = hit ? 1 : 0;
             if (!hit) continue;
@@ -498,34 +513,14 @@ __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned lo
 __global__ void __launch_bounds__(NP_BLOCK) k_hash_build(DevWorld w) {
     const unsigned int m = w.ctr->n_manifolds;
     const ManifoldSet cur = w.man[*w.cur_flip];
-    const unsigned int mask = w.cap_hash - 1u;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        uint2 k = cur.key[i];
-        unsigned long long key = ((unsigned long long) k.x << 32) | (unsigned long long) k.y;
-        unsigned int s = hash_slot(key, mask);
-        for (;;) {
-            unsigned long long prevk = atomicCAS(&w.h_key[s], HASH_EMPTY, key);
-            if (prevk == HASH_EMPTY || prevk == key) { w.h_val[s] = i; break; }
-            s = (s + 1u) & mask;
-        }
-    }
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) hash_insert(w, cur.key, i);
 }
 
 // after the table was re-allocated: index the PREVIOUS dense array again (warm-start lookups)
 __global__ void __launch_bounds__(NP_BLOCK) k_hash_build_prev(DevWorld w) {
     const unsigned int m = *w.prev_count;
     const ManifoldSet prev = w.man[*w.cur_flip ^ 1];
-    const unsigned int mask = w.cap_hash - 1u;
-    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) {
-        uint2 k = prev.key[i];
-        unsigned long long key = ((unsigned long long) k.x << 32) | (unsigned long long) k.y;
-        unsigned int s = hash_slot(key, mask);
-        for (;;) {
-            unsigned long long prevk = atomicCAS(&w.h_key[s], HASH_EMPTY, key);
-            if (prevk == HASH_EMPTY || prevk == key) { w.h_val[s] = i; break; }
-            s = (s + 1u) & mask;
-        }
-    }
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < m; i += gridDim.x * blockDim.x) hash_insert(w, prev.key, i);
 }
 
 static inline int grid_for(long long n, int block, int max_blocks) {
@@ -561,7 +556,7 @@ void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx) {
     if (w.sol_mult == 1u) k_carry_over<8><<<grid_for((long long) w.cap_manifolds, NP_BLOCK * 8, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7);
     else k_carry_over<1><<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w, cx.status[3], cx.tickets + 7);
     ++g_fx_launches;
-    cudaMemsetAsync(w.h_key, 0xff, (size_t) w.cap_hash * sizeof(unsigned long long), s);
+    cudaMemsetAsync(w.h_slot, 0xff, (size_t) w.cap_hash * sizeof(unsigned int), s);
     k_hash_build<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, s>>>(w); ++g_fx_launches;
 }
 

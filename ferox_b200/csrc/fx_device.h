@@ -14,7 +14,8 @@
 //             per contact slot (2*m+c): c_geo {point.x, point.y, depth, timestamp}
 //                                       c_imp {normalMass, normalScalar, tangentMass, tangentScalar}
 //                                       c_id
-//   hash map  open addressing, h_key (uidA<<32|uidB) -> h_val (index into the dense manifold array)
+//   hash map  open addressing over 4-byte slots holding an index into the dense manifold array; the key
+//             (uidA<<32|uidB) is compared through that array, so the table stays small enough for L2
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
@@ -148,8 +149,7 @@ struct DevWorld {
                          // last step's cache (read-only); k_finish_step flips the selector
     int *cur_flip;
     unsigned char *touched;              // per prev entry: probed (hit or miss) by this step
-    unsigned long long *h_key;
-    unsigned int *h_val;
+    unsigned int *h_slot;                // [cap_hash] index into the dense array the table was built over, ~0u: empty
     // solver
     SolverSet sol;
     unsigned int sol_stride, sol_mult;   // per-contact record (slot s, contact c) lives at c * sol_stride + s * sol_mult

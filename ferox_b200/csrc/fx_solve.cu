@@ -609,10 +609,12 @@ __device__ __forceinline__ int cache_lookup(const DevWorld &w, unsigned long lon
     const unsigned int mask = w.cap_hash - 1u;
     unsigned long long z = (key ^ (key >> 31)) * 0x9E3779B97F4A7C15ull;
     unsigned int s = (unsigned int) (z >> 32) & mask;
+    const uint2 *keys = w.man[*w.cur_flip].key;      // the table was just rebuilt over this step's array
     for (;;) {
-        unsigned long long k = w.h_key[s];
-        if (k == key) return (int) w.h_val[s];
-        if (k == 0xffffffffffffffffull) return -1;
+        const unsigned int v = w.h_slot[s];
+        if (v == 0xffffffffu) return -1;
+        const uint2 k = keys[v];
+        if ((((unsigned long long) k.x << 32) | (unsigned long long) k.y) == key) return (int) v;
         s = (s + 1u) & mask;
     }
 }

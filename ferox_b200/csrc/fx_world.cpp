@@ -153,7 +153,7 @@ static void world_free_device(frWorld *w) {
     cudaFree(d.keys[0]); cudaFree(d.keys[1]); cudaFree(d.vals[0]); cudaFree(d.vals[1]);
     cudaFree(d.cand); cudaFree(d.cand_hit);
     free_manifold_set(d.man[0]); free_manifold_set(d.man[1]);
-    cudaFree(d.touched); cudaFree(d.h_key); cudaFree(d.h_val);
+    cudaFree(d.touched); cudaFree(d.h_slot);
     cudaFree(d.sol.body); cudaFree(d.sol.nt); cudaFree(d.sol.mat); cudaFree(d.sol.count_src);
     cudaFree(d.sol.r); cudaFree(d.sol.u); cudaFree(d.sol.k); cudaFree(d.sol.lam);
     cudaFree(d.order); cudaFree(d.color_off); cudaFree(d.body_mask); cudaFree(d.body_dup); cudaFree(d.winner); cudaFree(d.cbody);
@@ -584,10 +584,10 @@ static bool ensure_work_capacity(frWorld *w, unsigned long long ent, unsigned lo
         // the hash map indexes the PREVIOUS dense array: rebuild it at the new size from that array
         unsigned int hcap = pow2_at_least(2ull * cap + 16);
         const unsigned int old_h = d.cap_hash;
-        ok = ok && dev_realloc(d.h_key, 0, hcap, s, false) && dev_realloc(d.h_val, 0, hcap, s, false);
+        ok = ok && dev_realloc(d.h_slot, 0, hcap, s, false);
         d.cap_hash = hcap;
         d.cap_manifolds = cap;
-        cudaMemsetAsync(d.h_key, 0xff, (size_t) hcap * sizeof(unsigned long long), s);
+        cudaMemsetAsync(d.h_slot, 0xff, (size_t) hcap * sizeof(unsigned int), s);
         if (old_h) fx_launch_rehash_prev(d, w->cx);
         changed = true;
     }
