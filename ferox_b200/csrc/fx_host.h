@@ -97,6 +97,7 @@ struct frWorld_ {
     HostMirror h;
     unsigned dirty = 0;
     bool device_newer = false;       // device state advanced past the host mirror
+    unsigned stale = 0;              // while device_newer was being consumed piecewise: FX_DIRTY_* bits of mirror arrays not yet downloaded
     bool needs_sizing = true;        // run the sizing pre-pass before the next step
     bool device_ok = false;
 
@@ -187,6 +188,7 @@ void fx_body_recompute_mass(frBody *b);
 BodyRow *fx_row(frBody *b);                 // current dynamic row for writing (pulls + marks dirty)
 const BodyRow fx_row_read(const frBody *b); // current dynamic row (pulls if the device is newer)
 void fx_world_pull(frWorld *w);
+void fx_world_pull_some(frWorld *w, unsigned want);   // want: FX_DIRTY_POSROT | _ANGLE | _VEL | _AABB
 void fx_world_mark(frWorld *w, unsigned bits);
 void fx_set_error(int code, const char *what);
 bool fx_cuda_ok(cudaError_t e, const char *what);

@@ -305,20 +305,30 @@ void fx_world_mark(frWorld *w, unsigned bits) {
 }
 
 // bring the pinned host mirror up to date with the device (one bulk D2H per dynamic array)
-void fx_world_pull(frWorld *w) {
-    if (!w || !w->device_newer) return;
-    w->device_newer = false;
+// Downloads the arrays of the host mirror that are stale AND wanted.  A step makes all four state arrays stale
+// (and the mirror's force accumulators, which the step cleared on the device).
+void fx_world_pull_some(frWorld *w, unsigned want) {
+    if (!w) return;
+    if (w->device_newer) {
+        w->device_newer = false;
+        w->stale = FX_DIRTY_POSROT | FX_DIRTY_ANGLE | FX_DIRTY_VEL | FX_DIRTY_AABB;
+        const size_t n0 = w->bodies.size();
+        if (n0) std::memset(w->h.force, 0, n0 * sizeof(float4));   // cleared by the step (src/world.c:481-482)
+    }
+    const unsigned get = w->stale & want;
     const size_t n = w->bodies.size();
+    if (!get) return;
+    w->stale &= ~get;
     if (n == 0 || !w->device_ok) return;
     cudaSetDevice(w->device);
     cudaStream_t s = w->stream;
-    cudaMemcpyAsync(w->h.posrot, w->dw.posrot, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(w->h.angle, w->dw.angle, n * sizeof(float), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(w->h.vel, w->dw.vel, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
-    cudaMemcpyAsync(w->h.aabb, w->dw.aabb, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    if (get & FX_DIRTY_POSROT) cudaMemcpyAsync(w->h.posrot, w->dw.posrot, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    if (get & FX_DIRTY_ANGLE) cudaMemcpyAsync(w->h.angle, w->dw.angle, n * sizeof(float), cudaMemcpyDeviceToHost, s);
+    if (get & FX_DIRTY_VEL) cudaMemcpyAsync(w->h.vel, w->dw.vel, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
+    if (get & FX_DIRTY_AABB) cudaMemcpyAsync(w->h.aabb, w->dw.aabb, n * sizeof(float4), cudaMemcpyDeviceToHost, s);
     fx_cuda_ok(cudaStreamSynchronize(s), "state download");
-    std::memset(w->h.force, 0, n * sizeof(float4));   // cleared by the step (src/world.c:481-482)
 }
+void fx_world_pull(frWorld *w) { fx_world_pull_some(w, FX_DIRTY_POSROT | FX_DIRTY_ANGLE | FX_DIRTY_VEL | FX_DIRTY_AABB); }
 
 // Per sub-world body index range (a plain world is one group).  The block-local solver stages a
 // group's velocities in shared memory, which needs the group's bodies in ONE short index range.
@@ -1504,7 +1514,9 @@ extern "C" int frxGetBodyStates(frWorld *w, float *position, float *angle, float
 extern "C" int frxViewBodyStates(frWorld *w, const float **posRot, const float **angle, const float **velocity, const float **aabb) {
     if (!w) return 0;
     if (w->device_ok) cudaSetDevice(w->device);
-    fx_world_pull(w);
+    // only the arrays asked for are downloaded (the others follow when a getter needs them)
+    fx_world_pull_some(w, (posRot ? FX_DIRTY_POSROT : 0u) | (angle ? FX_DIRTY_ANGLE : 0u) | (velocity ? FX_DIRTY_VEL : 0u) |
+                              (aabb ? FX_DIRTY_AABB : 0u));
     if (posRot) *posRot = reinterpret_cast<const float *>(w->h.posrot);
     if (angle) *angle = w->h.angle;
     if (velocity) *velocity = reinterpret_cast<const float *>(w->h.vel);
@@ -1515,7 +1527,7 @@ extern "C" int frxViewBodyStates(frWorld *w, const float **posRot, const float *
 extern "C" int frxMapBodyForces(frWorld *w, float **force) {
     if (!w || !force) return 0;
     if (w->device_ok) cudaSetDevice(w->device);
-    fx_world_pull(w);                      // also clears the mirror's accumulators if a step has run since
+    fx_world_pull_some(w, 0u);             // no download: only clears the mirror's accumulators if a step has run since
     *force = reinterpret_cast<float *>(w->h.force);
     w->dirty |= FX_DIRTY_FORCE;
     return (int) w->bodies.size();

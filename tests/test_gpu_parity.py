@@ -623,6 +623,18 @@ def test_state_views_equal_the_copying_getter(gpu):
         assert np.array_equal(v["angle"], st["angle"]) and np.array_equal(v["aabb"], st["aabb"])
         p = L.frGetBodyPosition(sc.bodies[7])
         assert (p.x, p.y) == (float(v["posrot"][7, 0]), float(v["posrot"][7, 1]))
+    # a view that asks for some arrays downloads only those; the rest follow when a getter needs them
+    import ctypes as C
+    L.frxStepWorldN(sc.world, DT, 5)
+    pp = C.POINTER(C.c_float)()
+    n = L.frxViewBodyStates(sc.world, C.byref(pp), None, None, None)
+    pos_only = np.ctypeslib.as_array(pp, shape=(n, 4)).copy()
+    box = L.frGetBodyAABB(sc.bodies[11])                      # stale array: must be fetched now
+    st = fb.body_states(L, sc.world)
+    assert np.array_equal(pos_only[:, :2], st["pos"])
+    assert (box.x, box.y, box.width, box.height) == tuple(float(x) for x in st["aabb"][11])
+    v = L.frGetBodyVelocity(sc.bodies[11])
+    assert (v.x, v.y) == tuple(float(x) for x in st["vel"][11])
     fb.check_error(L)
     sc.release()
 
