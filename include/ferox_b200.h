@@ -266,7 +266,9 @@ int frxGetBodyStates(frWorld *w, float *position, float *angle, float *sincos, f
 /* Zero-copy variant: downloads the state once (if the device is ahead) and returns READ-ONLY views of
    the library's pinned host mirror, valid until the next call that steps or edits the world:
    posRot float[n][4] = (x, y, sin, cos), angle float[n], velocity float[n][4] = (vx, vy, omega,
-   1/mass), aabb float[n][4] = (x, y, w, h).  This is what the per-body getters read.  Returns n. */
+   1/mass), aabb float[n][4] = (x, y, w, h).  This is what the per-body getters read.  Any of the four
+   may be NULL: only the arrays asked for are downloaded (the others follow when a getter needs them).
+   Returns n. */
 int frxViewBodyStates(frWorld *w, const float **posRot, const float **angle, const float **velocity, const float **aabb);
 /* Writable view of the force accumulators in the pinned host mirror: force float[n][4] = (fx, fy, torque, 0),
    zero after every step (src/world.c:481-482); whatever the caller ADDS here before the next step is uploaded
