@@ -29,7 +29,9 @@ extern long long g_fx_launches;
 #define FX_LARGE_CELLS 32u
 #define FX_MAX_CELLS_PER_BODY (1u << 24)
 
+#ifndef SORT_ITEMS
 #define SORT_ITEMS 8
+#endif
 #define SORT_TILE (BP_BLOCK * SORT_ITEMS)
 
 // packed entry value: [28:0] body index, 29: entry is in the body's min-x column, 30: min-y row,
