@@ -120,6 +120,15 @@ __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_
             mxx = max(mxx, __shfl_xor_sync(0xffffffffu, mxx, d));
             mxy = max(mxy, __shfl_xor_sync(0xffffffffu, mxy, d));
         }
+        unsigned int total;
+        unsigned int excl = block_exclusive_scan<BP_BLOCK>(cnt, &total);
+        unsigned int base = tile_exclusive_prefix(status, tile, total);
+        if (valid) {
+            w.cell_cnt[i] = cnt;
+            w.cell_off[i] = base + excl;
+        }
+        if ((int) tile == ntiles - 1 && threadIdx.x == 0) w.ctr->n_entries = base + total;
+        // (after the look-back: the tile's prefix is published before this warp waits for a look at the bounds)
         if (lane_id() == 0 && mnx <= mxx) {
             // the bounds only ever widen, so a plain look first is safe: after the first tiles almost no warp
             // needs its atomics ([measured] 1 M bodies: 131 k atomics on four addresses otherwise)
@@ -130,14 +139,6 @@ __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_
             if (mxx > vc->cell_max_x) atomicMax(&w.ctr->cell_max_x, mxx);
             if (mxy > vc->cell_max_y) atomicMax(&w.ctr->cell_max_y, mxy);
         }
-        unsigned int total;
-        unsigned int excl = block_exclusive_scan<BP_BLOCK>(cnt, &total);
-        unsigned int base = tile_exclusive_prefix(status, tile, total);
-        if (valid) {
-            w.cell_cnt[i] = cnt;
-            w.cell_off[i] = base + excl;
-        }
-        if ((int) tile == ntiles - 1 && threadIdx.x == 0) w.ctr->n_entries = base + total;
         (void) s_b;
     }
 }
