@@ -89,7 +89,6 @@ __global__ void __launch_bounds__(BP_BLOCK) k_integrate_velocity(DevWorld w) {
 
 __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_velocity, unsigned long long *status,
                                                            unsigned int *ticket) {
-    __shared__ int s_b[4];
     const int ntiles = (w.n + BP_BLOCK - 1) / BP_BLOCK;
     for (;;) {
         unsigned int tile = claim_tile(ticket);
@@ -139,7 +138,6 @@ __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_
             if (mxx > vc->cell_max_x) atomicMax(&w.ctr->cell_max_x, mxx);
             if (mxy > vc->cell_max_y) atomicMax(&w.ctr->cell_max_y, mxy);
         }
-        (void) s_b;
     }
 }
 

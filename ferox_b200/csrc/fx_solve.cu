@@ -59,10 +59,6 @@ __device__ __forceinline__ bool body_is_written(const DevWorld &w, int i) {
     return w.vel[i].w > 0.0f || w.mprop[i].y > 0.0f;
 }
 
-struct BodyS {
-    float4 v;   // vx, vy, omega, invMass
-};
-
 // build the solver record of manifold m at slot s and apply its warm start (src/rigid_body.c:333-411)
 __device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const ManifoldSet &man, unsigned int m,
                                                        unsigned int s, float4 *vel, int lo) {

@@ -1515,8 +1515,12 @@ extern "C" int frxViewBodyStates(frWorld *w, const float **posRot, const float *
     if (!w) return 0;
     if (w->device_ok) cudaSetDevice(w->device);
     // only the arrays asked for are downloaded (the others follow when a getter needs them)
-    fx_world_pull_some(w, (posRot ? FX_DIRTY_POSROT : 0u) | (angle ? FX_DIRTY_ANGLE : 0u) | (velocity ? FX_DIRTY_VEL : 0u) |
-                              (aabb ? FX_DIRTY_AABB : 0u));
+    unsigned want = 0u;
+    if (posRot) want |= FX_DIRTY_POSROT;
+    if (angle) want |= FX_DIRTY_ANGLE;
+    if (velocity) want |= FX_DIRTY_VEL;
+    if (aabb) want |= FX_DIRTY_AABB;
+    fx_world_pull_some(w, want);
     if (posRot) *posRot = reinterpret_cast<const float *>(w->h.posrot);
     if (angle) *angle = w->h.angle;
     if (velocity) *velocity = reinterpret_cast<const float *>(w->h.vel);
