@@ -90,4 +90,4 @@ void fx_launch_strip_stage_pack(const DevWorld &w, const FxLaunchCtx &cx, const 
                                 const float4 *border_before, const unsigned int *border_split, float4 *border_vel, unsigned int capacity);
 void fx_launch_strip_stage_apply(const DevWorld &w, const FxLaunchCtx &cx, const unsigned char *full_msg, const unsigned int *border_idx,
                                  const float4 *recv_delta, const float4 *recv_vel, const float4 *my_delta, const unsigned int *ghost_cnt,
-                                 unsigned int capacity);
+                                 float4 *ghost_before, float4 *border_before, unsigned int capacity);

@@ -138,59 +138,58 @@ __global__ void k_strip_scale_mass(DevWorld w, const float4 *flags, unsigned int
         w.mprop[i] = mp;
     }
 }
-// my left-border bodies before a solver stage
-__global__ void k_strip_snapshot_border(DevWorld w, const unsigned char *full_msg, const unsigned int *border_idx, float4 *before) {
-    const unsigned int count = *reinterpret_cast<const unsigned int *>(full_msg);
-    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) before[r] = w.vel[border_idx[r]];
+// Per solver stage a strip runs TWO small kernels around the exchange (one before the first stage):
+//   stage_begin  remembers the velocities of my ghosts and of my left-border bodies
+//   stage_pack   ghosts: what the stage did to each (sent right, to the owner; halved for mass-split rows);
+//                border bodies: their velocity after the stage (sent left); a mass-split body keeps only half of the
+//                change its (twice too light) copy received
+//   stage_apply  owner side: add the left neighbour's changes to my border bodies; ghost side: the owner's new
+//                velocity plus my own change = the same bits the owner ends up with; both results are also the
+//                "before" values of the next stage
+__global__ void k_strip_stage_begin(DevWorld w, float4 *ghost_before, const unsigned int *ghost_cnt, const unsigned char *full_msg,
+                                    const unsigned int *border_idx, float4 *border_before) {
+    const unsigned int ghosts = *ghost_cnt, border = *reinterpret_cast<const unsigned int *>(full_msg);
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < ghosts; r += gridDim.x * blockDim.x)
+        ghost_before[r] = w.vel[w.n_owned + (int) r];
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < border; r += gridDim.x * blockDim.x)
+        border_before[r] = w.vel[border_idx[r]];
 }
-// velocities of my left-border bodies after the stage, in message order (sent to the left neighbour);
-// mass-split bodies keep only half of the change their (twice too light) copy received
-__global__ void k_strip_pack_vel(DevWorld w, const unsigned char *full_msg, const unsigned int *border_idx, const float4 *before,
-                                 const unsigned int *split, float4 *out) {
-    const unsigned int count = *reinterpret_cast<const unsigned int *>(full_msg);
-    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
+__global__ void k_strip_stage_pack(DevWorld w, const float4 *ghost_before, const unsigned int *ghost_split, float4 *delta,
+                                   const unsigned int *ghost_cnt, const unsigned char *full_msg, const unsigned int *border_idx,
+                                   const float4 *border_before, const unsigned int *border_split, float4 *border_vel) {
+    const unsigned int ghosts = *ghost_cnt, border = *reinterpret_cast<const unsigned int *>(full_msg);
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < ghosts; r += gridDim.x * blockDim.x) {
+        const float4 a = w.vel[w.n_owned + (int) r], b = ghost_before[r];
+        const float k = ghost_split[r] ? 0.5f : 1.0f;
+        delta[r] = make_float4(k * (a.x - b.x), k * (a.y - b.y), k * (a.z - b.z), 0.0f);
+    }
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < border; r += gridDim.x * blockDim.x) {
         float4 v = w.vel[border_idx[r]];
-        if (split[r]) {
-            const float4 b = before[r];
+        if (border_split[r]) {
+            const float4 b = border_before[r];
             v.x = b.x + 0.5f * (v.x - b.x); v.y = b.y + 0.5f * (v.y - b.y); v.z = b.z + 0.5f * (v.z - b.z);
             w.vel[border_idx[r]] = v;
         }
-        out[r] = v;
+        border_vel[r] = v;
     }
 }
-// ghost velocities before a solver stage
-__global__ void k_strip_snapshot(DevWorld w, float4 *before, const unsigned int *ghost_cnt) {
-    const unsigned int count = *ghost_cnt;
-    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x)
-        before[r] = w.vel[w.n_owned + (int) r];
-}
-// what the stage did to each ghost (sent to the right neighbour, who owns it); halved for mass-split rows
-__global__ void k_strip_delta(DevWorld w, const float4 *before, const unsigned int *split, float4 *delta, const unsigned int *ghost_cnt) {
-    const unsigned int count = *ghost_cnt;
-    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
-        const float4 a = w.vel[w.n_owned + (int) r], b = before[r];
-        const float k = split[r] ? 0.5f : 1.0f;
-        delta[r] = make_float4(k * (a.x - b.x), k * (a.y - b.y), k * (a.z - b.z), 0.0f);
-    }
-}
-// owner side: add the left neighbour's changes to my border bodies
-__global__ void k_strip_apply_delta(DevWorld w, const unsigned char *full_msg, const unsigned int *border_idx, const float4 *delta) {
-    const unsigned int count = *reinterpret_cast<const unsigned int *>(full_msg);
-    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
+__global__ void k_strip_stage_apply(DevWorld w, const unsigned char *full_msg, const unsigned int *border_idx, const float4 *recv_delta,
+                                    const float4 *recv_vel, const float4 *my_delta, const unsigned int *ghost_cnt,
+                                    float4 *ghost_before, float4 *border_before) {
+    const unsigned int ghosts = *ghost_cnt, border = *reinterpret_cast<const unsigned int *>(full_msg);
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < border; r += gridDim.x * blockDim.x) {
         float4 v = w.vel[border_idx[r]];
-        const float4 d = delta[r];
+        const float4 d = recv_delta[r];
         v.x = v.x + d.x; v.y = v.y + d.y; v.z = v.z + d.z;
         w.vel[border_idx[r]] = v;
+        border_before[r] = v;
     }
-}
-// ghost side: the owner's new velocity plus my own change = the same bits the owner ends up with
-__global__ void k_strip_ghost_update(DevWorld w, const float4 *owner_vel, const float4 *my_delta, const unsigned int *ghost_cnt) {
-    const unsigned int count = *ghost_cnt;
-    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < count; r += gridDim.x * blockDim.x) {
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < ghosts; r += gridDim.x * blockDim.x) {
         float4 v = w.vel[w.n_owned + (int) r];          // keeps the (possibly split) inverse mass in .w
-        const float4 o = owner_vel[r], d = my_delta[r];
+        const float4 o = recv_vel[r], d = my_delta[r];
         v.x = o.x + d.x; v.y = o.y + d.y; v.z = o.z + d.z;
         w.vel[w.n_owned + (int) r] = v;
+        ghost_before[r] = v;
     }
 }
 
@@ -232,21 +231,20 @@ void fx_launch_strip_scale_mass(const DevWorld &w, const FxLaunchCtx &cx, const 
 }
 void fx_launch_strip_stage_begin(const DevWorld &w, const FxLaunchCtx &cx, float4 *ghost_before, const unsigned int *ghost_cnt,
                                  const unsigned char *full_msg, const unsigned int *border_idx, float4 *border_before, unsigned int capacity) {
-    const int g = grid_for(capacity, ST_BLOCK, cx.max_blocks);
-    k_strip_snapshot<<<g, ST_BLOCK, 0, cx.stream>>>(w, ghost_before, ghost_cnt); ++g_fx_launches;
-    k_strip_snapshot_border<<<g, ST_BLOCK, 0, cx.stream>>>(w, full_msg, border_idx, border_before); ++g_fx_launches;
+    k_strip_stage_begin<<<grid_for(capacity, ST_BLOCK, cx.max_blocks), ST_BLOCK, 0, cx.stream>>>(w, ghost_before, ghost_cnt, full_msg, border_idx, border_before);
+    ++g_fx_launches;
 }
 void fx_launch_strip_stage_pack(const DevWorld &w, const FxLaunchCtx &cx, const float4 *ghost_before, const unsigned int *ghost_split, float4 *delta,
                                 const unsigned int *ghost_cnt, const unsigned char *full_msg, const unsigned int *border_idx,
                                 const float4 *border_before, const unsigned int *border_split, float4 *border_vel, unsigned int capacity) {
-    const int g = grid_for(capacity, ST_BLOCK, cx.max_blocks);
-    k_strip_delta<<<g, ST_BLOCK, 0, cx.stream>>>(w, ghost_before, ghost_split, delta, ghost_cnt); ++g_fx_launches;
-    k_strip_pack_vel<<<g, ST_BLOCK, 0, cx.stream>>>(w, full_msg, border_idx, border_before, border_split, border_vel); ++g_fx_launches;
+    k_strip_stage_pack<<<grid_for(capacity, ST_BLOCK, cx.max_blocks), ST_BLOCK, 0, cx.stream>>>(w, ghost_before, ghost_split, delta, ghost_cnt, full_msg,
+                                                                                           border_idx, border_before, border_split, border_vel);
+    ++g_fx_launches;
 }
 void fx_launch_strip_stage_apply(const DevWorld &w, const FxLaunchCtx &cx, const unsigned char *full_msg, const unsigned int *border_idx,
                                  const float4 *recv_delta, const float4 *recv_vel, const float4 *my_delta, const unsigned int *ghost_cnt,
-                                 unsigned int capacity) {
-    const int g = grid_for(capacity, ST_BLOCK, cx.max_blocks);
-    k_strip_apply_delta<<<g, ST_BLOCK, 0, cx.stream>>>(w, full_msg, border_idx, recv_delta); ++g_fx_launches;
-    k_strip_ghost_update<<<g, ST_BLOCK, 0, cx.stream>>>(w, recv_vel, my_delta, ghost_cnt); ++g_fx_launches;
+                                 float4 *ghost_before, float4 *border_before, unsigned int capacity) {
+    k_strip_stage_apply<<<grid_for(capacity, ST_BLOCK, cx.max_blocks), ST_BLOCK, 0, cx.stream>>>(w, full_msg, border_idx, recv_delta, recv_vel, my_delta, ghost_cnt,
+                                                                                            ghost_before, border_before);
+    ++g_fx_launches;
 }

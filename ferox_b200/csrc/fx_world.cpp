@@ -1180,7 +1180,8 @@ static void strip_stage_sync(frWorld **ws, int n) {
         frWorld *w = ws[k];
         cudaSetDevice(w->device);
         frWorld_::Strip &st = w->strip;
-        fx_launch_strip_stage_apply(w->dw, w->cx, st.send_full, st.border_idx, st.recv_delta, st.recv_vel, st.send_delta, st.ghost_cnt, st.ghost_cap);
+        fx_launch_strip_stage_apply(w->dw, w->cx, st.send_full, st.border_idx, st.recv_delta, st.recv_vel, st.send_delta, st.ghost_cnt,
+                                    st.ghost_before, st.border_before, st.ghost_cap);
         cudaEventRecord(st.consumed, w->stream);
     }
 }
@@ -1261,8 +1262,7 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
             cudaSetDevice(w->device);
             frWorld_::Strip &st = w->strip;
             const long long hint = w->manifold_hint > (long long) w->dw.n ? w->manifold_hint : (long long) w->dw.n;
-            fx_launch_strip_stage_begin(w->dw, w->cx, st.ghost_before, st.ghost_cnt, st.send_full, st.border_idx, st.border_before, st.ghost_cap);
-            fx_launch_solve_colored(w->dw, w->cx, 1, hint, 2 /* one sweep */);
+            fx_launch_solve_colored(w->dw, w->cx, 1, hint, 2 /* one sweep */);      // "before" values: written by the last stage_apply
         }
         strip_stage_sync(ws, n);
     }
