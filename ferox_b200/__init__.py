@@ -61,6 +61,7 @@ EXT_PROTOTYPES = {
     "frxGetStepCounters": (None, [P, C.POINTER(StepCounters)]),
     "frxGetBodyStates": (I, [P, P, P, P, P, P, P]),
     "frxViewBodyStates": (I, [P, P, P, P, P]),
+    "frxClearLastError": (None, []),
     "frxMapBodyForces": (I, [P, P]),
     "frxApplyForces": (I, [P, P, P, I]),
     "frxSetBodyVelocities": (I, [P, P, P, I]),

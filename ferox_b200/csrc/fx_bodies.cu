@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(BD_BLOCK) k_integrate_position(DevWorld w) {
 __global__ void k_begin_step(DevWorld w) {
     StepCountersDev *c = w.ctr;
     c->n_entries = c->n_cand = c->n_hits = c->n_manifolds = c->n_contacts = c->n_colors = 0u;
-    c->overflow = 0u;
+    c->overflow &= (32u | 128u);      // a strip's border pack runs BEFORE this kernel: keep what it reported (cleared by k_finish_step)
     c->sort_passes = 0u;
     c->cell_min_x = c->cell_min_y = 0x7fffffff;
     c->cell_max_x = c->cell_max_y = (int) 0x80000000;
@@ -85,6 +85,7 @@ __global__ void k_finish_step(DevWorld w, StepCountersDev *snapshot) {
     w.prev_count[1] = w.ctr->n_colors;              // the colouring squeezes its top colours next step (fx_solve.cu)
     *w.cur_flip ^= 1;
     *snapshot = *w.ctr;
+    w.ctr->overflow = 0u;
 }
 
 static inline int grid_for(long long n, int block, int max_blocks) {

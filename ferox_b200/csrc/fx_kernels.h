@@ -74,7 +74,7 @@ void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o);
 void fx_launch_collide_pairs(const DevWorld &w, const FxLaunchCtx &cx, const int2 *pairs, int n, Manifold *out);
 
 // strip decomposition (fx_strip.cu)
-void fx_launch_strip_pack(const DevWorld &w, const FxLaunchCtx &cx, int side, float cut, float margin, unsigned char *msg,
+void fx_launch_strip_pack(const DevWorld &w, const FxLaunchCtx &cx, int side, float cut, float margin, float stray_lo, float stray_hi, unsigned char *msg,
                           unsigned int *border_idx, unsigned int capacity);
 void fx_launch_strip_clear_ghost_map(const DevWorld &w, const FxLaunchCtx &cx, int first_row, int rows);
 void fx_launch_strip_unpack(const DevWorld &w, const FxLaunchCtx &cx, const unsigned char *msg, int first_row, unsigned int capacity,

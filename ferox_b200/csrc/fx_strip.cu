@@ -31,8 +31,10 @@ extern long long g_fx_launches;
 #define ST_BLOCK 256
 
 // ordered compaction of the border bodies of one side into `msg`; remembers their indices
+// Also flags (overflow bit 128) an owned body whose position lies outside [stray_lo, stray_hi] = the strip widened by
+// the margin: ownership is static, such a body has lost its cross-cut contacts.
 __global__ void __launch_bounds__(ST_BLOCK) k_strip_pack(DevWorld w, int side, float cut, float margin, unsigned char *msg,
-                                                         unsigned int *border_idx, unsigned int capacity,
+                                                         unsigned int *border_idx, unsigned int capacity, float stray_lo, float stray_hi,
                                                          unsigned long long *status, unsigned int *ticket) {
     GhostRow *rows = reinterpret_cast<GhostRow *>(msg + FX_MSG_HEADER);
     const int ntiles = (w.n_owned + ST_BLOCK - 1) / ST_BLOCK;
@@ -46,7 +48,11 @@ __global__ void __launch_bounds__(ST_BLOCK) k_strip_pack(DevWorld w, int side, f
             const int type = __float_as_int(w.mprop[i].w) & 0xff;
             const float4 a = w.aabb[i];
             // static bodies are replicated on every rank by construction, never exchanged
-            if (type != FX_BODY_STATIC) take = (side == 0) ? (a.x < cut + margin) : (a.x + a.z > cut - margin);
+            if (type != FX_BODY_STATIC) {
+                take = (side == 0) ? (a.x < cut + margin) : (a.x + a.z > cut - margin);
+                const float px = w.posrot[i].x;          // the position, not the AABB (a state of its own, App. A.9)
+                if (px < stray_lo || px > stray_hi) atomicOr(&w.ctr->overflow, 128u);
+            }
         }
         unsigned int total;
         const unsigned int excl = block_exclusive_scan<ST_BLOCK>(take ? 1u : 0u, &total);
@@ -200,13 +206,13 @@ static inline int grid_for(long long n, int block, int max_blocks) {
     return (int) g;
 }
 
-void fx_launch_strip_pack(const DevWorld &w, const FxLaunchCtx &cx, int side, float cut, float margin, unsigned char *msg,
+void fx_launch_strip_pack(const DevWorld &w, const FxLaunchCtx &cx, int side, float cut, float margin, float stray_lo, float stray_hi, unsigned char *msg,
                           unsigned int *border_idx, unsigned int capacity) {
     // the body-prepass status words / ticket are free here (begin_step clears them again afterwards)
     cudaMemsetAsync(cx.status[0], 0, cx.status_words[0] * sizeof(unsigned long long), cx.stream);
     cudaMemsetAsync(cx.tickets, 0, sizeof(unsigned int), cx.stream);
     k_strip_pack<<<grid_for(w.n_owned, ST_BLOCK, cx.max_blocks), ST_BLOCK, 0, cx.stream>>>(w, side, cut, margin, msg, border_idx, capacity,
-                                                                                         cx.status[0], cx.tickets);
+                                                                                         stray_lo, stray_hi, cx.status[0], cx.tickets);
     ++g_fx_launches;
 }
 void fx_launch_strip_clear_ghost_map(const DevWorld &w, const FxLaunchCtx &cx, int first_row, int rows) {

@@ -37,6 +37,7 @@ bool fx_cuda_ok(cudaError_t e, const char *what) {
     return false;
 }
 extern "C" int frxGetLastError(void) { return g_error; }
+extern "C" void frxClearLastError(void) { g_error = 0; g_error_text[0] = 0; }
 extern "C" const char *frxGetLastErrorString(void) { return g_error_text; }
 extern "C" int frxSetDevice(int device) {
     int n = 0;
@@ -690,12 +691,13 @@ static void read_snapshot(frWorld *w, bool wait) {
     w->snapshot_pending = false;
     w->last = *w->h_snapshot;
     w->manifold_hint = w->last.n_manifolds;
-    if (w->last.overflow) {
-        w->sticky_overflow |= w->last.overflow;
-        char buf[200];
+    // bit 128 (a body outside its strip, static ownership) is a condition the caller reads from the counters, not lost work
+    w->sticky_overflow |= w->last.overflow;
+    if (w->last.overflow & ~128u) {
+        char buf[260];
         std::snprintf(buf, sizeof buf,
                       "device buffer overflow in step %lld (mask 0x%x: 1 cell entries, 2 candidates, 4 manifolds, 8 colours, 16 "
-                      "cell-key range); work was dropped",
+                      "cell-key range, 32 ghost rows); work was dropped",
                       w->steps, w->last.overflow);
         fx_set_error(2, buf);
     }
@@ -1210,7 +1212,9 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
         if (w->cx.zero_base == nullptr && !ensure_work_capacity(w, 8ull * rows + 4096, 16ull * rows + 4096, 4ull * rows + 4096)) return;
         fill_dev_params(w, dt);
         const bool has_left = st.peer[0] != nullptr || (st.nccl_comm && st.rank > 0);
-        if (has_left) fx_launch_strip_pack(w->dw, w->cx, 0, st.cut_lo, st.margin, st.send_full, st.border_idx, st.ghost_cap);
+        // without a left neighbour the cut is -inf: nothing is packed, but the kernel still checks for stray bodies
+        fx_launch_strip_pack(w->dw, w->cx, 0, has_left ? st.cut_lo : -INFINITY, st.margin, st.cut_lo - st.margin, st.cut_hi + st.margin,
+                             st.send_full, st.border_idx, st.ghost_cap);
     }
     strip_exchange(ws, n, 0);
     // ---- ghosts in, then everything up to and including the warm start

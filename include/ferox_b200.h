@@ -226,6 +226,7 @@ int frxSetDevice(int device);
 /* 0 = no error; otherwise the sticky code of the first CUDA/capacity failure.  frxGetLastErrorString
    returns a static description. */
 int frxGetLastError(void);
+void frxClearLastError(void);      /* the error is sticky: the first one is kept until cleared */
 const char *frxGetLastErrorString(void);
 
 /* Capacity: the reference fixes the body count at compile time (FR_WORLD_MAX_OBJECT_COUNT,

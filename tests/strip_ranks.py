@@ -72,7 +72,7 @@ def main():
     mine &= dyn
     y = got["pos"][mine, 1].astype(np.float64)
     v2 = (got["vel"][mine].astype(np.float64) ** 2).sum(1)
-    sums = torch.tensor([y.sum(), float(mine.sum()), v2.sum(), float(ctr["manifolds"]), float(ctr["overflow"] != 0),
+    sums = torch.tensor([y.sum(), float(mine.sum()), v2.sum(), float(ctr["manifolds"]), float((ctr["overflow"] & ~128) != 0),
                          float(np.isfinite(got["pos"][mine]).all())], dtype=torch.float64, device=dev)
     ymax = torch.tensor([y.max() if len(y) else -1e30], dtype=torch.float64, device=dev)
     dist.all_reduce(sums)
