@@ -11,7 +11,7 @@
 //                    world cell bounds (atomics), exclusive offsets via decoupled look-back scan
 //   k_plan           1 thread: dense key geometry (grid_w/h, key bits, radix passes)
 //   k_emit_entries   per body: (cellKey, packedBody) for every covered cell; bodies covering more
-//   k_emit_large     than FX_LARGE_CELLS cells are expanded by a whole block each (e.g. a ground
+//                    than FX_LARGE_CELLS cells are expanded by a whole block each (e.g. a ground
 //                    plane spanning thousands of cells)
 //   k_sort_hist + k_sort_pass (x passes)  onesweep-style LSD radix sort, 8-bit digits, one kernel
 //                    per digit with chained-scan look-back per digit; stable, deterministic
@@ -169,6 +169,13 @@ __global__ void k_plan(DevWorld w) {
     while (bits < 32 && (1ull << bits) < cells * groups) ++bits;
     c->key_bits = bits;
     c->sort_passes = (bits + 7) / 8;
+    if ((int) c->sort_passes > (w.sort_launch > 0 ? w.sort_launch : 4)) {
+        // the host launched fewer digit passes than these keys need (it sizes them from the previous step's key width
+        // plus one bit): the world's extent more than doubled within one step.  Refuse loudly, emit nothing.
+        c->overflow |= 16u;
+        c->n_entries = 0;
+        c->sort_passes = 0;
+    }
 }
 
 __device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, int x, int y, const CellRect &r,
@@ -182,11 +189,27 @@ __device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, 
     w.vals[0][pos] = v;
 }
 
-__global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w) {
+// the last `large_blocks` blocks of the grid expand the bodies that cover more than FX_LARGE_CELLS cells (ground
+// planes spanning thousands of cells), one body per block at a time; the others take one ordinary body per thread
+__global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large_blocks) {
     const int minx = w.ctr->cell_min_x, miny = w.ctr->cell_min_y;
     const unsigned int gw = w.ctr->grid_w;
     if (w.ctr->overflow & 16u) return;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
+    const int body_blocks = (int) gridDim.x - large_blocks;
+    if ((int) blockIdx.x >= body_blocks) {
+        const unsigned int nl = w.ctr->n_large;
+        for (unsigned int l = blockIdx.x - body_blocks; l < nl; l += (unsigned int) large_blocks) {
+            unsigned int i = w.large_list[l];
+            CellRect r = body_rect(w.aabb[i], w.inv_cell);
+            unsigned int rw = (unsigned int) (r.x1 - r.x0 + 1);
+            unsigned int cnt = w.cell_cnt[i], pos = w.cell_off[i];
+            unsigned int massbit = (w.vel[i].w > 0.0f && (int) i < w.n_owned) ? ENT_MASS : 0u;
+            for (unsigned int t = threadIdx.x; t < cnt; t += blockDim.x)
+                emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw);
+        }
+        return;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += body_blocks * blockDim.x) {
         unsigned int cnt = w.cell_cnt[i];
         if (cnt == 0u || cnt > FX_LARGE_CELLS) continue;
         CellRect r = body_rect(w.aabb[i], w.inv_cell);
@@ -195,22 +218,6 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w) {
         unsigned int massbit = (w.vel[i].w > 0.0f && i < w.n_owned) ? ENT_MASS : 0u;
         for (int y = r.y0; y <= r.y1; ++y)
             for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw);
-    }
-}
-
-__global__ void __launch_bounds__(BP_BLOCK) k_emit_large(DevWorld w) {
-    const int minx = w.ctr->cell_min_x, miny = w.ctr->cell_min_y;
-    const unsigned int gw = w.ctr->grid_w;
-    if (w.ctr->overflow & 16u) return;
-    const unsigned int nl = w.ctr->n_large;
-    for (unsigned int l = blockIdx.x; l < nl; l += gridDim.x) {
-        unsigned int i = w.large_list[l];
-        CellRect r = body_rect(w.aabb[i], w.inv_cell);
-        unsigned int rw = (unsigned int) (r.x1 - r.x0 + 1);
-        unsigned int cnt = w.cell_cnt[i], pos = w.cell_off[i];
-        unsigned int massbit = (w.vel[i].w > 0.0f && (int) i < w.n_owned) ? ENT_MASS : 0u;
-        for (unsigned int t = threadIdx.x; t < cnt; t += blockDim.x)
-            emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw);
     }
 }
 
@@ -431,14 +438,13 @@ void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_ve
     const int G = cx.max_blocks;
     k_body_prepass<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, fuse_velocity ? 1 : 0, cx.status[0], cx.tickets + 0); ++g_fx_launches;
     k_plan<<<1, 1, 0, s>>>(w); ++g_fx_launches;
-    k_emit_entries<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w); ++g_fx_launches;
-    k_emit_large<<<64, BP_BLOCK, 0, s>>>(w); ++g_fx_launches;
+    k_emit_entries<<<grid_for(w.n, BP_BLOCK, G) + 64, BP_BLOCK, 0, s>>>(w, 64); ++g_fx_launches;
     SortJob job;
     job.keys[0] = w.keys[0]; job.keys[1] = w.keys[1]; job.vals[0] = w.vals[0]; job.vals[1] = w.vals[1];
     job.n = &w.ctr->n_entries; job.passes_dev = &w.ctr->sort_passes; job.passes = 4;
     job.ghist = cx.sort_hist; job.dstatus = cx.digit_status; job.dstatus_stride = cx.digit_status_stride;
     job.tickets = cx.tickets + 8;
-    launch_sort(job, (long long) w.cap_entries, 4, G, s);
+    launch_sort(job, (long long) w.cap_entries, w.sort_launch > 0 && w.sort_launch < 4 ? w.sort_launch : 4, G, s);
     if (w.sol_mult == 1u) k_emit_pairs<4><<<grid_for((long long) w.cap_entries, BP_BLOCK * 4, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);   // large world
     else k_emit_pairs<1><<<grid_for((long long) w.cap_entries, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);
     ++g_fx_launches;

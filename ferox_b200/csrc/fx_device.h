@@ -121,6 +121,7 @@ struct DevWorld {
     float timestamp;
     float dt, inv_dt;
     int solver_mode;
+    int sort_launch;     // radix-sort passes the host launches this step (k_plan refuses a world whose keys need more)
     int color_squeeze;   // how many of last step's top colours are re-coloured every step (0: never)
     int narrow_mode;     // 0: one lane per pair (default), 1: 8 lanes per pair with shuffle arg-max over axes
     // bodies

@@ -660,6 +660,13 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.dt = dt;
     d.inv_dt = 1.0f / dt;                                       // src/world.c:242
     d.solver_mode = w->solver_mode;
+    {
+        // digit passes of the broadphase sort: all four until a step has told us the key width, then what that width
+        // plus one bit needs (k_plan refuses a step whose keys need more than was launched)
+        const unsigned int bits = w->last.key_bits;
+        d.sort_launch = (bits == 0u || w->needs_sizing) ? 4 : (int) ((bits + 1u + 7u) / 8u);
+        if (d.sort_launch > 4) d.sort_launch = 4;
+    }
     { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }
     {
         // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
@@ -693,6 +700,7 @@ static void read_snapshot(frWorld *w, bool wait) {
     w->manifold_hint = w->last.n_manifolds;
     // bit 128 (a body outside its strip, static ownership) is a condition the caller reads from the counters, not lost work
     w->sticky_overflow |= w->last.overflow;
+    if (w->last.overflow & 16u) w->needs_sizing = true;      // next step: all four sort passes, buffers re-measured
     if (w->last.overflow & ~128u) {
         char buf[260];
         std::snprintf(buf, sizeof buf,
@@ -728,6 +736,7 @@ static bool sizing_prepass(frWorld *w, float dt) {
         unsigned long long want_e = 2ull * c.n_entries + 4096, want_c = 2ull * c.n_cand + 4096;
         unsigned long long want_m = (unsigned long long) c.n_cand + 2ull * w->last.n_manifolds + 4096;
         if (want_m > want_c) want_m = want_c + w->last.n_manifolds;
+        w->last.key_bits = c.key_bits;       // measured on this very state: the step sizes its sort passes from it
         return ensure_work_capacity(w, want_e, want_c, want_m);
     }
     fx_set_error(4, "could not size the broadphase buffers");
