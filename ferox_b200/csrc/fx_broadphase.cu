@@ -9,8 +9,8 @@
 // Stages (all sizes live on the device; no host round trip inside a step):
 //   k_body_prepass   per body: [gravity + velocity integration], cell rectangle, cells covered,
 //                    world cell bounds (atomics), exclusive offsets via decoupled look-back scan
-//   k_plan           1 thread: dense key geometry (grid_w/h, key bits, radix passes)
-//   k_emit_entries   per body: (cellKey, packedBody) for every covered cell; bodies covering more
+//   k_emit_entries   dense key geometry (grid_w/h, key bits, radix passes: plan_keys), then per body:
+//                    (cellKey, packedBody) for every covered cell; bodies covering more
 //                    than FX_LARGE_CELLS cells are expanded by a whole block each (e.g. a ground
 //                    plane spanning thousands of cells)
 //   k_sort_hist + k_sort_pass (x passes)  onesweep-style LSD radix sort, 8-bit digits, one kernel
@@ -141,49 +141,62 @@ __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_
     }
 }
 
-__global__ void k_plan(DevWorld w) {
+// Dense key geometry (grid_w/h, key bits, radix passes) from the world cell bounds the prepass left behind.  Every
+// block of k_emit_entries evaluates it (a few dozen integer operations) instead of waiting for a one-thread kernel;
+// `publish` (one thread of the grid) also stores it for the kernels that follow.  Returns false when nothing may be
+// emitted this step.
+__device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsigned int *out_gw, unsigned int *out_gh) {
     StepCountersDev *c = w.ctr;
-    if (c->n_entries > w.cap_entries) {
-        c->overflow |= 1u;
-        c->n_entries = w.cap_entries;
-    }
-    if (c->n_large > w.cap_large) { c->overflow |= 1u; c->n_large = w.cap_large; }
+    unsigned int flags = 0u;
+    unsigned int n_entries = c->n_entries, n_large = c->n_large;
+    if (n_entries > w.cap_entries) { flags |= 1u; n_entries = w.cap_entries; }
+    if (n_large > w.cap_large) { flags |= 1u; n_large = w.cap_large; }
     unsigned long long gw = 1, gh = 1;
-    if (c->cell_min_x <= c->cell_max_x) {
-        gw = (unsigned long long) ((long long) c->cell_max_x - c->cell_min_x + 1);
-        gh = (unsigned long long) ((long long) c->cell_max_y - c->cell_min_y + 1);
+    const int mnx = c->cell_min_x, mny = c->cell_min_y, mxx = c->cell_max_x, mxy = c->cell_max_y;
+    if (mnx <= mxx) {
+        gw = (unsigned long long) ((long long) mxx - mnx + 1);
+        gh = (unsigned long long) ((long long) mxy - mny + 1);
     }
     unsigned long long cells = gw * gh;
     const unsigned long long groups = (w.group != nullptr && w.n_groups > 1) ? (unsigned long long) w.n_groups : 1ull;
     // batched worlds: the key is group * (W*H) + cell, so bodies of different sub-worlds never share a run
+    bool ok = true;
     if (gw > 0xffffffffull || gh > 0xffffffffull || cells > 0x100000000ull || cells * groups > 0x100000000ull) {
         // the dense key does not fit 32 bits: refuse loudly (host reports it), emit nothing
-        c->overflow |= 16u;
-        c->n_entries = 0;
+        ok = false;
         gw = gh = 1;
         cells = 1;
     }
-    c->grid_w = (unsigned int) gw;
-    c->grid_h = (unsigned int) gh;
     unsigned int bits = 1;
     while (bits < 32 && (1ull << bits) < cells * groups) ++bits;
-    c->key_bits = bits;
-    c->sort_passes = (bits + 7) / 8;
-    if ((int) c->sort_passes > (w.sort_launch > 0 ? w.sort_launch : 4)) {
+    unsigned int passes = (bits + 7) / 8;
+    if ((int) passes > (w.sort_launch > 0 ? w.sort_launch : 4)) {
         // the host launched fewer digit passes than these keys need (it sizes them from the previous step's key width
         // plus one bit): the world's extent more than doubled within one step.  Refuse loudly, emit nothing.
-        c->overflow |= 16u;
-        c->n_entries = 0;
-        c->sort_passes = 0;
+        ok = false;
+        passes = 0;
     }
+    if (!ok) { flags |= 16u; n_entries = 0; }
+    if (publish) {
+        if (flags) atomicOr(&c->overflow, flags);
+        c->n_entries = n_entries;
+        c->n_large = n_large;
+        c->grid_w = (unsigned int) gw;
+        c->grid_h = (unsigned int) gh;
+        c->key_bits = bits;
+        c->sort_passes = passes;
+    }
+    *out_gw = (unsigned int) gw;
+    *out_gh = (unsigned int) gh;
+    return ok;
 }
 
 __device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, int x, int y, const CellRect &r,
                                            unsigned int body, unsigned int massbit, int minx, int miny,
-                                           unsigned int gw) {
+                                           unsigned int gw, unsigned int gh) {
     if (pos >= w.cap_entries) return;
     unsigned int key = (unsigned int) (y - miny) * gw + (unsigned int) (x - minx);
-    if (w.group != nullptr) key += (unsigned int) w.group[body] * (gw * w.ctr->grid_h);
+    if (w.group != nullptr) key += (unsigned int) w.group[body] * (gw * gh);
     unsigned int v = body | massbit | (x == r.x0 ? ENT_X0 : 0u) | (y == r.y0 ? ENT_Y0 : 0u);
     w.keys[0][pos] = key;
     w.vals[0][pos] = v;
@@ -193,11 +206,18 @@ __device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, 
 // planes spanning thousands of cells), one body per block at a time; the others take one ordinary body per thread
 __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large_blocks) {
     const int minx = w.ctr->cell_min_x, miny = w.ctr->cell_min_y;
-    const unsigned int gw = w.ctr->grid_w;
-    if (w.ctr->overflow & 16u) return;
+    __shared__ unsigned int s_plan[3];
+    if (threadIdx.x == 0) {
+        unsigned int pgw, pgh;
+        const bool ok = plan_keys(w, blockIdx.x == 0, &pgw, &pgh);
+        s_plan[0] = pgw; s_plan[1] = pgh; s_plan[2] = ok ? 1u : 0u;
+    }
+    __syncthreads();
+    const unsigned int gw = s_plan[0], gh = s_plan[1];
+    if (!s_plan[2]) return;
     const int body_blocks = (int) gridDim.x - large_blocks;
     if ((int) blockIdx.x >= body_blocks) {
-        const unsigned int nl = w.ctr->n_large;
+        const unsigned int nl = min(w.ctr->n_large, w.cap_large);
         for (unsigned int l = blockIdx.x - body_blocks; l < nl; l += (unsigned int) large_blocks) {
             unsigned int i = w.large_list[l];
             CellRect r = body_rect(w.aabb[i], w.inv_cell);
@@ -205,7 +225,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large
             unsigned int cnt = w.cell_cnt[i], pos = w.cell_off[i];
             unsigned int massbit = (w.vel[i].w > 0.0f && (int) i < w.n_owned) ? ENT_MASS : 0u;
             for (unsigned int t = threadIdx.x; t < cnt; t += blockDim.x)
-                emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw);
+                emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw, gh);
         }
         return;
     }
@@ -217,7 +237,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large
         // ghost rows never count as 'has mass': ghost/ghost and ghost/static pairs belong to the owner
         unsigned int massbit = (w.vel[i].w > 0.0f && i < w.n_owned) ? ENT_MASS : 0u;
         for (int y = r.y0; y <= r.y1; ++y)
-            for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw);
+            for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw, gh);
     }
 }
 
@@ -437,7 +457,6 @@ void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_ve
     cudaStream_t s = cx.stream;
     const int G = cx.max_blocks;
     k_body_prepass<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, fuse_velocity ? 1 : 0, cx.status[0], cx.tickets + 0); ++g_fx_launches;
-    k_plan<<<1, 1, 0, s>>>(w); ++g_fx_launches;
     k_emit_entries<<<grid_for(w.n, BP_BLOCK, G) + 64, BP_BLOCK, 0, s>>>(w, 64); ++g_fx_launches;
     SortJob job;
     job.keys[0] = w.keys[0]; job.keys[1] = w.keys[1]; job.vals[0] = w.vals[0]; job.vals[1] = w.vals[1];
