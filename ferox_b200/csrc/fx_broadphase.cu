@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_
 // block of k_emit_entries evaluates it (a few dozen integer operations) instead of waiting for a one-thread kernel;
 // `publish` (one thread of the grid) also stores it for the kernels that follow.  Returns false when nothing may be
 // emitted this step.
-__device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsigned int *out_gw, unsigned int *out_gh) {
+__device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsigned int *out_gw, unsigned int *out_gh, unsigned int *out_passes) {
     StepCountersDev *c = w.ctr;
     unsigned int flags = 0u;
     unsigned int n_entries = c->n_entries, n_large = c->n_large;
@@ -188,32 +188,37 @@ __device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsig
     }
     *out_gw = (unsigned int) gw;
     *out_gh = (unsigned int) gh;
+    *out_passes = passes;
     return ok;
 }
 
 __device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, int x, int y, const CellRect &r,
                                            unsigned int body, unsigned int massbit, int minx, int miny,
-                                           unsigned int gw, unsigned int gh) {
+                                           unsigned int gw, unsigned int gh, unsigned int (*hist)[256], unsigned int passes) {
     if (pos >= w.cap_entries) return;
     unsigned int key = (unsigned int) (y - miny) * gw + (unsigned int) (x - minx);
     if (w.group != nullptr) key += (unsigned int) w.group[body] * (gw * gh);
     unsigned int v = body | massbit | (x == r.x0 ? ENT_X0 : 0u) | (y == r.y0 ? ENT_Y0 : 0u);
     w.keys[0][pos] = key;
     w.vals[0][pos] = v;
+    // the digit histograms of the radix sort are counted here, while the key is at hand (no separate pass over the keys)
+    for (unsigned int p = 0; p < passes; ++p) atomicAdd(&hist[p][(key >> (8u * p)) & 255u], 1u);
 }
 
 // the last `large_blocks` blocks of the grid expand the bodies that cover more than FX_LARGE_CELLS cells (ground
 // planes spanning thousands of cells), one body per block at a time; the others take one ordinary body per thread
-__global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large_blocks) {
+__global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large_blocks, unsigned int *ghist) {
     const int minx = w.ctr->cell_min_x, miny = w.ctr->cell_min_y;
-    __shared__ unsigned int s_plan[3];
+    __shared__ unsigned int s_plan[4];
+    __shared__ unsigned int s_h[4][256];
+    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) (&s_h[0][0])[t] = 0u;
     if (threadIdx.x == 0) {
-        unsigned int pgw, pgh;
-        const bool ok = plan_keys(w, blockIdx.x == 0, &pgw, &pgh);
-        s_plan[0] = pgw; s_plan[1] = pgh; s_plan[2] = ok ? 1u : 0u;
+        unsigned int pgw, pgh, pp;
+        const bool ok = plan_keys(w, blockIdx.x == 0, &pgw, &pgh, &pp);
+        s_plan[0] = pgw; s_plan[1] = pgh; s_plan[2] = ok ? 1u : 0u; s_plan[3] = pp;
     }
     __syncthreads();
-    const unsigned int gw = s_plan[0], gh = s_plan[1];
+    const unsigned int gw = s_plan[0], gh = s_plan[1], passes = s_plan[3];
     if (!s_plan[2]) return;
     const int body_blocks = (int) gridDim.x - large_blocks;
     if ((int) blockIdx.x >= body_blocks) {
@@ -225,10 +230,9 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large
             unsigned int cnt = w.cell_cnt[i], pos = w.cell_off[i];
             unsigned int massbit = (w.vel[i].w > 0.0f && (int) i < w.n_owned) ? ENT_MASS : 0u;
             for (unsigned int t = threadIdx.x; t < cnt; t += blockDim.x)
-                emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw, gh);
+                emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw, gh, s_h, passes);
         }
-        return;
-    }
+    } else
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += body_blocks * blockDim.x) {
         unsigned int cnt = w.cell_cnt[i];
         if (cnt == 0u || cnt > FX_LARGE_CELLS) continue;
@@ -237,7 +241,12 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large
         // ghost rows never count as 'has mass': ghost/ghost and ghost/static pairs belong to the owner
         unsigned int massbit = (w.vel[i].w > 0.0f && i < w.n_owned) ? ENT_MASS : 0u;
         for (int y = r.y0; y <= r.y1; ++y)
-            for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw, gh);
+            for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw, gh, s_h, passes);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) {
+        const unsigned int v = (&s_h[0][0])[t];
+        if (v) atomicAdd(&ghist[t], v);
     }
 }
 
@@ -348,11 +357,11 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
     }
 }
 
-static void launch_sort(const SortJob &job, long long cap, int max_passes, int max_blocks, cudaStream_t s) {
+static void launch_sort(const SortJob &job, long long cap, int max_passes, int max_blocks, cudaStream_t s, bool with_hist = true) {
     long long gh = (cap + BP_BLOCK * 8 - 1) / (BP_BLOCK * 8), gp = (cap + SORT_TILE - 1) / SORT_TILE;
     int gridh = (int) (gh < 1 ? 1 : (gh > max_blocks ? max_blocks : gh));
     int gridp = (int) (gp < 1 ? 1 : (gp > max_blocks ? max_blocks : gp));
-    k_sort_hist<<<gridh, BP_BLOCK, 0, s>>>(job); ++g_fx_launches;
+    if (with_hist) { k_sort_hist<<<gridh, BP_BLOCK, 0, s>>>(job); ++g_fx_launches; }
     for (int p = 0; p < max_passes; ++p) { k_sort_pass<<<gridp, BP_BLOCK, 0, s>>>(job, p); ++g_fx_launches; }
 }
 
@@ -457,13 +466,13 @@ void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_ve
     cudaStream_t s = cx.stream;
     const int G = cx.max_blocks;
     k_body_prepass<<<grid_for(w.n, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, fuse_velocity ? 1 : 0, cx.status[0], cx.tickets + 0); ++g_fx_launches;
-    k_emit_entries<<<grid_for(w.n, BP_BLOCK, G) + 64, BP_BLOCK, 0, s>>>(w, 64); ++g_fx_launches;
+    k_emit_entries<<<grid_for(w.n, BP_BLOCK, G) + 64, BP_BLOCK, 0, s>>>(w, 64, cx.sort_hist); ++g_fx_launches;
     SortJob job;
     job.keys[0] = w.keys[0]; job.keys[1] = w.keys[1]; job.vals[0] = w.vals[0]; job.vals[1] = w.vals[1];
     job.n = &w.ctr->n_entries; job.passes_dev = &w.ctr->sort_passes; job.passes = 4;
     job.ghist = cx.sort_hist; job.dstatus = cx.digit_status; job.dstatus_stride = cx.digit_status_stride;
     job.tickets = cx.tickets + 8;
-    launch_sort(job, (long long) w.cap_entries, w.sort_launch > 0 && w.sort_launch < 4 ? w.sort_launch : 4, G, s);
+    launch_sort(job, (long long) w.cap_entries, w.sort_launch > 0 && w.sort_launch < 4 ? w.sort_launch : 4, G, s, false /* histograms: k_emit_entries */);
     if (w.sol_mult == 1u) k_emit_pairs<4><<<grid_for((long long) w.cap_entries, BP_BLOCK * 4, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);   // large world
     else k_emit_pairs<1><<<grid_for((long long) w.cap_entries, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);
     ++g_fx_launches;
