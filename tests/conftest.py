@@ -28,8 +28,11 @@ def ref():
 
 @pytest.fixture(scope="session")
 def prod():
-    """The product library; loading it needs no GPU, stepping does."""
+    """The product library; loading it needs no GPU, stepping does.  A fresh checkout has no built artefacts
+    (they are git-ignored): compile them first, exactly as __graft_entry__.build() does."""
     import ferox_b200 as fb
+    if not os.path.exists(fb.LIB_PATH):
+        fb.build()
     return fb.lib()
 
 
