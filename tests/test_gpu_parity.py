@@ -693,3 +693,35 @@ def test_mapped_forces_equal_apply_force_calls(gpu):
         sc.release()
     for k in ("pos", "angle", "vel", "omega"):
         assert np.array_equal(out[0][k].view(np.uint32), out[1][k].view(np.uint32)), k
+
+
+def test_update_world_accumulator_matches_reference_with_a_fake_clock(gpu, ref):
+    """frUpdateWorld (src/world.c:268-285): the first call latches the clock, later calls run
+    floor(accumulator / dt) steps and stamp contacts with the world clock (which arms the eviction rule,
+    :222-235).  A preloaded deterministic frGetCurrentTime drives the reference and the product through
+    the same 40 calls (0, 1 or 2 steps each); reference-order mode must end bit-identical."""
+    import hashlib, os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(tempfile.mkdtemp(), "libfake_clock.so")
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(root, "tests", "c", "fake_clock.c")])
+    code = ("import sys, hashlib, numpy as np\n"
+            "from ferox_b200 import capi, scenes\n"
+            "import ferox_b200 as fb\n"
+            "kind = sys.argv[1]\n"
+            "L = fb.lib() if kind == 'gpu' else capi.load_abi(sys.argv[2])\n"
+            "if kind == 'gpu': L.frxSetDevice(0)\n"
+            "sc = scenes.Scene(L, scenes.mixed_pile(300, width=30.0), prime=False)\n"
+            "if kind == 'gpu': L.frxSetWorldSolverMode(sc.world, fb.SOLVER_SERIAL)\n"
+            "for k in range(40): L.frUpdateWorld(sc.world, scenes.DT)\n"
+            "st = scenes.snapshot(L, sc.bodies)\n"
+            "print('HASH', hashlib.sha1(b''.join(st[k].tobytes() for k in ('pos', 'angle', 'vel', 'omega'))).hexdigest(),"
+            " L.frGetBodyCountInWorld(sc.world), float(st['pos'][:, 1].mean()))\n")
+    from tests.conftest import ref_path
+    out = []
+    for kind in ("ref", "gpu"):
+        env = dict(os.environ, LD_PRELOAD=so, PYTHONPATH=root)
+        r = subprocess.run([sys.executable, "-c", code, kind, ref_path(8192)], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][-1])
+    assert out[0] == out[1], out
+    assert int(out[0].split()[2]) == 303          # the bodies did enter the world (a call ran at least one step)
