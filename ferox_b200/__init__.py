@@ -76,6 +76,7 @@ EXT_PROTOTYPES = {
     "frxRecordEvent": (None, [P, I]),
     "frxEventElapsedMs": (F, [P, I, I]),
     "frxGetLaunchCount": (C.c_longlong, []),
+    "frxGetGraphReplays": (C.c_longlong, [P]),
     "frxProfilerRange": (None, [I]),
     "frxTimedSteps": (I, [P, F, I, I, f32p]),
 }

@@ -61,8 +61,9 @@ __device__ __forceinline__ void integrate_position_one(const DevWorld &w, int i,
 }
 
 __global__ void __launch_bounds__(BD_BLOCK) k_integrate_position(DevWorld w) {
+    const float dt = w.scal->dt;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n_owned; i += gridDim.x * blockDim.x) {
-        integrate_position_one(w, i, w.dt);
+        integrate_position_one(w, i, dt);
         w.force[i] = make_float4(0.f, 0.f, 0.f, 0.f);    // frClearBodyForces, world.c:481-482
     }
 }
@@ -95,8 +96,16 @@ static inline int grid_for(long long n, int block, int max_blocks) {
     return (int) g;
 }
 
+__global__ void k_set_scalars(StepScalars *dst, StepScalars v) { *dst = v; }
+void fx_launch_set_scalars(StepScalars *dst, const StepScalars &v, cudaStream_t s) {
+    k_set_scalars<<<1, 1, 0, s>>>(dst, v); ++g_fx_launches;
+}
+
 void fx_launch_begin_step(const DevWorld &w, const FxLaunchCtx &cx) {
-    cudaMemsetAsync(cx.zero_base, 0, cx.zero_bytes, cx.stream);
+    const size_t planes = (size_t) (w.sort_launch > 0 && w.sort_launch < FX_SORT_MAX_PASSES ? w.sort_launch : FX_SORT_MAX_PASSES);
+    size_t bytes = cx.zero_fixed_bytes + planes * cx.digit_status_stride * sizeof(unsigned int);
+    if (bytes > cx.zero_bytes) bytes = cx.zero_bytes;
+    cudaMemsetAsync(cx.zero_base, 0, bytes, cx.stream);
     k_begin_step<<<1, 1, 0, cx.stream>>>(w); ++g_fx_launches;
 }
 

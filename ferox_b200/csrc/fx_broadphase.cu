@@ -82,14 +82,27 @@ __device__ __forceinline__ float4 integrate_velocity(float4 v, float4 mp, float4
     return v;
 }
 
-__global__ void __launch_bounds__(BP_BLOCK) k_integrate_velocity(DevWorld w) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x)
-        w.vel[i] = integrate_velocity(w.vel[i], w.mprop[i], w.force[i], w.gx, w.gy, w.dt);
+// store_force: the accumulators keep the gravity term, as the reference's do until frPostStepWorld clears them
+// (src/rigid_body.c:309-316); only a world with a collision handler can observe that (frGetBodyForce in postStep)
+__global__ void __launch_bounds__(BP_BLOCK) k_integrate_velocity(DevWorld w, int store_force) {
+    const StepScalars sc = *w.scal;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += gridDim.x * blockDim.x) {
+        const float4 mp = w.mprop[i];
+        float4 f = w.force[i];
+        w.vel[i] = integrate_velocity(w.vel[i], mp, f, sc.gx, sc.gy, sc.dt);
+        if (store_force && mp.x > 0.0f) {
+            const float k = mp.z * mp.x;
+            f.x = f.x + sc.gx * k;
+            f.y = f.y + sc.gy * k;
+            w.force[i] = f;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_velocity, unsigned long long *status,
                                                            unsigned int *ticket) {
     const int ntiles = (w.n + BP_BLOCK - 1) / BP_BLOCK;
+    const StepScalars sc = *w.scal;
     for (;;) {
         unsigned int tile = claim_tile(ticket);
         if ((int) tile >= ntiles) return;
@@ -99,7 +112,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_
         bool valid = i < w.n;
         if (valid) {
             if (fuse_velocity)
-                w.vel[i] = integrate_velocity(w.vel[i], w.mprop[i], w.force[i], w.gx, w.gy, w.dt);
+                w.vel[i] = integrate_velocity(w.vel[i], w.mprop[i], w.force[i], sc.gx, sc.gy, sc.dt);
             CellRect rr = body_rect(w.aabb[i], w.inv_cell);
             bool bad;
             cnt = rect_cells(rr, &bad);
@@ -145,7 +158,8 @@ __global__ void __launch_bounds__(BP_BLOCK) k_body_prepass(DevWorld w, int fuse_
 // block of k_emit_entries evaluates it (a few dozen integer operations) instead of waiting for a one-thread kernel;
 // `publish` (one thread of the grid) also stores it for the kernels that follow.  Returns false when nothing may be
 // emitted this step.
-__device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsigned int *out_gw, unsigned int *out_gh, unsigned int *out_passes) {
+__device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsigned long long *out_gw, unsigned long long *out_cells,
+                                          unsigned int *out_passes, unsigned int *out_bits) {
     StepCountersDev *c = w.ctr;
     unsigned int flags = 0u;
     unsigned int n_entries = c->n_entries, n_large = c->n_large;
@@ -157,22 +171,24 @@ __device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsig
         gw = (unsigned long long) ((long long) mxx - mnx + 1);
         gh = (unsigned long long) ((long long) mxy - mny + 1);
     }
-    unsigned long long cells = gw * gh;
     const unsigned long long groups = (w.group != nullptr && w.n_groups > 1) ? (unsigned long long) w.n_groups : 1ull;
-    // batched worlds: the key is group * (W*H) + cell, so bodies of different sub-worlds never share a run
+    // The key is DENSE -- group * (W*H) + (y - ymin) * W + (x - xmin), so bodies of different sub-worlds never share a
+    // run -- and 64 bits wide: the reference's hash is keyed by (x, y) and has no extent limit
+    // (src/broad_phase.c:99-127), so a body thrown far away must not be able to refuse the step.  Worlds whose key
+    // fits 32 bits (every pile) never touch the high words; the radix sort runs ceil(bits / 8) digit passes.
     bool ok = true;
-    if (gw > 0xffffffffull || gh > 0xffffffffull || cells > 0x100000000ull || cells * groups > 0x100000000ull) {
-        // the dense key does not fit 32 bits: refuse loudly (host reports it), emit nothing
-        ok = false;
+    unsigned long long cells = 1;
+    if (gh > (1ull << 62) / gw || gw * gh > (1ull << 62) / groups) {
+        ok = false;                         // > 2^62 cells: both extents beyond 2^31 cells, i.e. non-finite coordinates
         gw = gh = 1;
-        cells = 1;
-    }
+    } else cells = gw * gh;
     unsigned int bits = 1;
-    while (bits < 32 && (1ull << bits) < cells * groups) ++bits;
+    while (bits < 63 && (1ull << bits) < cells * groups) ++bits;
     unsigned int passes = (bits + 7) / 8;
-    if ((int) passes > (w.sort_launch > 0 ? w.sort_launch : 4)) {
+    if ((int) passes > (w.sort_launch > 0 ? w.sort_launch : 8)) {
         // the host launched fewer digit passes than these keys need (it sizes them from the previous step's key width
-        // plus one bit): the world's extent more than doubled within one step.  Refuse loudly, emit nothing.
+        // plus one bit, and launches all eight after any setter moved a body): the world's extent more than doubled
+        // within one step of free motion.  Refuse loudly, emit nothing; the next step re-measures.
         ok = false;
         passes = 0;
     }
@@ -181,45 +197,55 @@ __device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsig
         if (flags) atomicOr(&c->overflow, flags);
         c->n_entries = n_entries;
         c->n_large = n_large;
-        c->grid_w = (unsigned int) gw;
-        c->grid_h = (unsigned int) gh;
+        c->grid_w = (unsigned int) (gw > 0xffffffffull ? 0xffffffffull : gw);
+        c->grid_h = (unsigned int) (gh > 0xffffffffull ? 0xffffffffull : gh);
         c->key_bits = bits;
         c->sort_passes = passes;
     }
-    *out_gw = (unsigned int) gw;
-    *out_gh = (unsigned int) gh;
+    *out_gw = gw;
+    *out_cells = cells;
     *out_passes = passes;
+    *out_bits = bits;
     return ok;
 }
 
+struct KeyPlan {
+    unsigned long long gw, cells;
+    unsigned int passes, wide;     // wide: the key needs more than 32 bits (the high words are live)
+    int minx, miny;
+};
+
 __device__ __forceinline__ void emit_entry(const DevWorld &w, unsigned int pos, int x, int y, const CellRect &r,
-                                           unsigned int body, unsigned int massbit, int minx, int miny,
-                                           unsigned int gw, unsigned int gh, unsigned int (*hist)[256], unsigned int passes) {
+                                           unsigned int body, unsigned int massbit, const KeyPlan &kp, unsigned int (*hist)[256]) {
     if (pos >= w.cap_entries) return;
-    unsigned int key = (unsigned int) (y - miny) * gw + (unsigned int) (x - minx);
-    if (w.group != nullptr) key += (unsigned int) w.group[body] * (gw * gh);
+    unsigned long long key = (unsigned long long) ((unsigned int) y - (unsigned int) kp.miny) * kp.gw +
+                             (unsigned long long) ((unsigned int) x - (unsigned int) kp.minx);
+    if (w.group != nullptr) key += (unsigned long long) w.group[body] * kp.cells;
     unsigned int v = body | massbit | (x == r.x0 ? ENT_X0 : 0u) | (y == r.y0 ? ENT_Y0 : 0u);
-    w.keys[0][pos] = key;
+    w.keys[0][pos] = (unsigned int) key;
+    if (kp.wide) w.keys_hi[0][pos] = (unsigned int) (key >> 32);
     w.vals[0][pos] = v;
     // the digit histograms of the radix sort are counted here, while the key is at hand (no separate pass over the keys)
-    for (unsigned int p = 0; p < passes; ++p) atomicAdd(&hist[p][(key >> (8u * p)) & 255u], 1u);
+    for (unsigned int p = 0; p < kp.passes; ++p) atomicAdd(&hist[p][(unsigned int) (key >> (8u * p)) & 255u], 1u);
 }
 
 // the last `large_blocks` blocks of the grid expand the bodies that cover more than FX_LARGE_CELLS cells (ground
 // planes spanning thousands of cells), one body per block at a time; the others take one ordinary body per thread
 __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large_blocks, unsigned int *ghist) {
-    const int minx = w.ctr->cell_min_x, miny = w.ctr->cell_min_y;
-    __shared__ unsigned int s_plan[4];
-    __shared__ unsigned int s_h[4][256];
-    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) (&s_h[0][0])[t] = 0u;
+    __shared__ KeyPlan s_kp;
+    __shared__ unsigned int s_ok;
+    __shared__ unsigned int s_h[FX_SORT_MAX_PASSES][256];
+    for (int t = threadIdx.x; t < FX_SORT_MAX_PASSES * 256; t += blockDim.x) (&s_h[0][0])[t] = 0u;
     if (threadIdx.x == 0) {
-        unsigned int pgw, pgh, pp;
-        const bool ok = plan_keys(w, blockIdx.x == 0, &pgw, &pgh, &pp);
-        s_plan[0] = pgw; s_plan[1] = pgh; s_plan[2] = ok ? 1u : 0u; s_plan[3] = pp;
+        unsigned int bits;
+        s_ok = plan_keys(w, blockIdx.x == 0, &s_kp.gw, &s_kp.cells, &s_kp.passes, &bits) ? 1u : 0u;
+        s_kp.wide = bits > 32u ? 1u : 0u;
+        s_kp.minx = w.ctr->cell_min_x;
+        s_kp.miny = w.ctr->cell_min_y;
     }
     __syncthreads();
-    const unsigned int gw = s_plan[0], gh = s_plan[1], passes = s_plan[3];
-    if (!s_plan[2]) return;
+    if (!s_ok) return;
+    const KeyPlan kp = s_kp;
     const int body_blocks = (int) gridDim.x - large_blocks;
     if ((int) blockIdx.x >= body_blocks) {
         const unsigned int nl = min(w.ctr->n_large, w.cap_large);
@@ -230,7 +256,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large
             unsigned int cnt = w.cell_cnt[i], pos = w.cell_off[i];
             unsigned int massbit = (w.vel[i].w > 0.0f && (int) i < w.n_owned) ? ENT_MASS : 0u;
             for (unsigned int t = threadIdx.x; t < cnt; t += blockDim.x)
-                emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, minx, miny, gw, gh, s_h, passes);
+                emit_entry(w, pos + t, r.x0 + (int) (t % rw), r.y0 + (int) (t / rw), r, i, massbit, kp, s_h);
         }
     } else
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < w.n; i += body_blocks * blockDim.x) {
@@ -241,10 +267,10 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large
         // ghost rows never count as 'has mass': ghost/ghost and ghost/static pairs belong to the owner
         unsigned int massbit = (w.vel[i].w > 0.0f && i < w.n_owned) ? ENT_MASS : 0u;
         for (int y = r.y0; y <= r.y1; ++y)
-            for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, minx, miny, gw, gh, s_h, passes);
+            for (int x = r.x0; x <= r.x1; ++x) emit_entry(w, pos++, x, y, r, (unsigned int) i, massbit, kp, s_h);
     }
     __syncthreads();
-    for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) {
+    for (int t = threadIdx.x; t < (int) kp.passes * 256; t += blockDim.x) {
         const unsigned int v = (&s_h[0][0])[t];
         if (v) atomicAdd(&ghist[t], v);
     }
@@ -254,9 +280,9 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_entries(DevWorld w, int large
 // radix sort of (key, value) entries
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(BP_BLOCK) k_sort_hist(SortJob job) {
-    __shared__ unsigned int s_h[4][256];
+    __shared__ unsigned int s_h[4][256];     // 32-bit keys only (the candidate ordering of the parity mode)
     const unsigned int n = *job.n;
-    const unsigned int passes = job.passes_dev ? *job.passes_dev : job.passes;
+    const unsigned int passes = min(job.passes_dev ? *job.passes_dev : job.passes, 4u);
     for (int t = threadIdx.x; t < 4 * 256; t += blockDim.x) (&s_h[0][0])[t] = 0u;
     __syncthreads();
     const unsigned int *keys = job.keys[0];
@@ -282,11 +308,16 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
     const unsigned int n = *job.n;
     const unsigned int passes = job.passes_dev ? *job.passes_dev : job.passes;
     if ((unsigned int) pass >= passes) return;
+    // wide keys (> 32 bits): the high words travel with the entries; passes 4..7 take their digit from them
+    const bool wide = job.bits_dev != nullptr && *job.bits_dev > 32u;
     const unsigned int *kin = job.keys[pass & 1], *vin = job.vals[pass & 1];
     unsigned int *kout = job.keys[(pass + 1) & 1], *vout = job.vals[(pass + 1) & 1];
+    const unsigned int *hin = wide ? job.keys_hi[pass & 1] : nullptr;
+    unsigned int *hout = wide ? job.keys_hi[(pass + 1) & 1] : nullptr;
+    const bool hi_digit = pass >= 4;
     unsigned int *dstatus = job.dstatus + (size_t) pass * job.dstatus_stride;
     unsigned int *ticket = job.tickets + pass;
-    const unsigned int shift = 8u * (unsigned int) pass;
+    const unsigned int shift = 8u * (unsigned int) (pass & 3);
     const unsigned int ntiles = (n + SORT_TILE - 1) / SORT_TILE;
     const unsigned int warp = threadIdx.x >> 5, lane = lane_id();
 
@@ -299,15 +330,16 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
         if (tile >= ntiles) return;
         for (int t = threadIdx.x; t < (BP_BLOCK / 32) * 256; t += blockDim.x) (&s_wc[0][0])[t] = 0u;
         __syncthreads();
-        unsigned int key[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
+        unsigned int key[SORT_ITEMS], khi[SORT_ITEMS], val[SORT_ITEMS], rank[SORT_ITEMS];
         const unsigned int base = tile * SORT_TILE + warp * (32 * SORT_ITEMS);
 #pragma unroll
         for (int j = 0; j < SORT_ITEMS; ++j) {
             unsigned int e = base + j * 32 + lane;
             bool ok = e < n;
             key[j] = ok ? kin[e] : 0xffffffffu;
+            khi[j] = (ok && wide) ? hin[e] : 0u;
             val[j] = ok ? vin[e] : 0u;
-            unsigned int d = (key[j] >> shift) & 255u;
+            unsigned int d = ((hi_digit ? khi[j] : key[j]) >> shift) & 255u;
             unsigned int m = ok ? d : (256u + lane);
             unsigned int peers = __match_any_sync(0xffffffffu, m);
             unsigned int before = __popc(peers & ((1u << lane) - 1u));
@@ -348,9 +380,10 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
         for (int j = 0; j < SORT_ITEMS; ++j) {
             unsigned int e = base + j * 32 + lane;
             if (e < n) {
-                unsigned int dd = (key[j] >> shift) & 255u;
+                unsigned int dd = ((hi_digit ? khi[j] : key[j]) >> shift) & 255u;
                 unsigned int pos = s_gb[dd] + s_wc[warp][dd] + rank[j];
                 kout[pos] = key[j];
+                if (wide) hout[pos] = khi[j];
                 vout[pos] = val[j];
             }
         }
@@ -402,6 +435,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_pairs(DevWorld w, unsigned lo
     const unsigned int n = w.ctr->n_entries;
     const unsigned int sel = w.ctr->sort_passes & 1u;
     const unsigned int *keys = w.keys[sel], *vals = w.vals[sel];
+    const unsigned int *khi = w.ctr->key_bits > 32u ? w.keys_hi[sel] : nullptr;      // wide keys: a run shares both words
     const unsigned int tile_size = BP_BLOCK * ITEMS;
     const unsigned int ntiles = (n + tile_size - 1) / tile_size;
     if (ntiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.ctr->n_cand = 0;
@@ -415,8 +449,8 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_pairs(DevWorld w, unsigned lo
             const unsigned int e = first + j;
             cnt[j] = 0u;
             if (e < n) {
-                const unsigned int k = keys[e], v = vals[e];
-                for (unsigned int f = e + 1; f < n && keys[f] == k; ++f) cnt[j] += pair_ok(v, vals[f]) ? 1u : 0u;
+                const unsigned int k = keys[e], v = vals[e], kh = khi ? khi[e] : 0u;
+                for (unsigned int f = e + 1; f < n && keys[f] == k && (!khi || khi[f] == kh); ++f) cnt[j] += pair_ok(v, vals[f]) ? 1u : 0u;
             }
             sum += cnt[j];
         }
@@ -428,8 +462,8 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_pairs(DevWorld w, unsigned lo
         for (int j = 0; j < ITEMS; ++j) {
             if (!cnt[j]) continue;
             const unsigned int e = first + j;
-            const unsigned int k = keys[e], v = vals[e];
-            for (unsigned int f = e + 1; f < n && keys[f] == k; ++f) {
+            const unsigned int k = keys[e], v = vals[e], kh = khi ? khi[e] : 0u;
+            for (unsigned int f = e + 1; f < n && keys[f] == k && (!khi || khi[f] == kh); ++f) {
                 unsigned int vf = vals[f];
                 if (pair_ok(v, vf)) {
                     // entries of one cell are in ascending body order (stable sort of an ascending
@@ -457,9 +491,9 @@ static inline int grid_for(long long n, int block, int max_blocks) {
     return (int) g;
 }
 
-void fx_launch_integrate_velocity(const DevWorld &w, const FxLaunchCtx &cx) {
+void fx_launch_integrate_velocity(const DevWorld &w, const FxLaunchCtx &cx, bool store_force) {
     if (w.n == 0) return;
-    k_integrate_velocity<<<grid_for(w.n, BP_BLOCK, cx.max_blocks), BP_BLOCK, 0, cx.stream>>>(w); ++g_fx_launches;
+    k_integrate_velocity<<<grid_for(w.n, BP_BLOCK, cx.max_blocks), BP_BLOCK, 0, cx.stream>>>(w, store_force ? 1 : 0); ++g_fx_launches;
 }
 
 void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_velocity) {
@@ -469,10 +503,12 @@ void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_ve
     k_emit_entries<<<grid_for(w.n, BP_BLOCK, G) + 64, BP_BLOCK, 0, s>>>(w, 64, cx.sort_hist); ++g_fx_launches;
     SortJob job;
     job.keys[0] = w.keys[0]; job.keys[1] = w.keys[1]; job.vals[0] = w.vals[0]; job.vals[1] = w.vals[1];
-    job.n = &w.ctr->n_entries; job.passes_dev = &w.ctr->sort_passes; job.passes = 4;
+    job.keys_hi[0] = w.keys_hi[0]; job.keys_hi[1] = w.keys_hi[1]; job.bits_dev = &w.ctr->key_bits;
+    job.n = &w.ctr->n_entries; job.passes_dev = &w.ctr->sort_passes; job.passes = FX_SORT_MAX_PASSES;
     job.ghist = cx.sort_hist; job.dstatus = cx.digit_status; job.dstatus_stride = cx.digit_status_stride;
     job.tickets = cx.tickets + 8;
-    launch_sort(job, (long long) w.cap_entries, w.sort_launch > 0 && w.sort_launch < 4 ? w.sort_launch : 4, G, s, false /* histograms: k_emit_entries */);
+    launch_sort(job, (long long) w.cap_entries, w.sort_launch > 0 && w.sort_launch < FX_SORT_MAX_PASSES ? w.sort_launch : FX_SORT_MAX_PASSES, G, s,
+                false /* histograms: k_emit_entries */);
     if (w.sol_mult == 1u) k_emit_pairs<4><<<grid_for((long long) w.cap_entries, BP_BLOCK * 4, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);   // large world
     else k_emit_pairs<1><<<grid_for((long long) w.cap_entries, BP_BLOCK, G), BP_BLOCK, 0, s>>>(w, cx.status[1], cx.tickets + 1);
     ++g_fx_launches;
@@ -493,6 +529,7 @@ void fx_launch_lexsort_candidates(const DevWorld &w, const FxLaunchCtx &cx, cons
         if (round == 1) { k_lex_mid<<<g, BP_BLOCK, 0, s>>>(w, lex.vals[src], lex.keys[src]); ++g_fx_launches; }
         job.keys[0] = lex.keys[src]; job.keys[1] = lex.keys[src ^ 1];
         job.vals[0] = lex.vals[src]; job.vals[1] = lex.vals[src ^ 1];
+        job.keys_hi[0] = job.keys_hi[1] = nullptr; job.bits_dev = nullptr;
         job.n = &w.ctr->n_cand; job.passes_dev = nullptr; job.passes = (unsigned int) passes;
         job.ghist = lex.ghist + round * 1024; job.dstatus = lex.dstatus + (size_t) round * 4 * lex.dstatus_stride;
         job.dstatus_stride = lex.dstatus_stride; job.tickets = lex.tickets + round * 4;

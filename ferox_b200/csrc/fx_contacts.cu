@@ -187,6 +187,7 @@ union NarrowStage {
 __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned long long *status, unsigned int *ticket) {
     __shared__ NarrowStage s_stage;
     const unsigned int ncand = w.ctr->n_cand;
+    const float stamp = w.scal->timestamp;
     const unsigned int ntiles = (ncand + NP_BLOCK - 1) / NP_BLOCK;
     const int cs = *w.cur_flip;
     const ManifoldSet cur = w.man[cs], prev = w.man[cs ^ 1];
@@ -252,8 +253,8 @@ __global__ void __launch_bounds__(NP_BLOCK) k_narrowphase(DevWorld w, unsigned l
                 cur.meta[pos] = make_int2(m.count, color);
                 // contacts[1] of a one-point manifold is a copy taken BEFORE stamping / warm-start
                 // transfer (src/collision.c:292,374,...; src/world.c:362-394): id/point/depth only
-                cur.geo[2 * pos] = make_float4(m.p[0].x, m.p[0].y, m.depth[0], w.timestamp);
-                cur.geo[2 * pos + 1] = make_float4(m.p[1].x, m.p[1].y, m.depth[1], (m.count > 1) ? w.timestamp : 0.0f);
+                cur.geo[2 * pos] = make_float4(m.p[0].x, m.p[0].y, m.depth[0], stamp);
+                cur.geo[2 * pos + 1] = make_float4(m.p[1].x, m.p[1].y, m.depth[1], (m.count > 1) ? stamp : 0.0f);
                 cur.imp[2 * pos] = make_float4(0.0f, lam_n[0], 0.0f, lam_t[0]);
                 cur.imp[2 * pos + 1] = make_float4(0.0f, (m.count > 1) ? lam_n[1] : 0.0f, 0.0f, (m.count > 1) ? lam_t[1] : 0.0f);
                 cur.cid[2 * pos] = m.id[0];
@@ -310,6 +311,7 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
     unsigned short *list_pp = list_cp + NP2_TILE;
     __shared__ unsigned int s_ncp, s_npp;
     const unsigned int ncand = w.ctr->n_cand;
+    const float stamp = w.scal->timestamp;
     const unsigned int ntiles = (ncand + NP2_TILE - 1) / NP2_TILE;
     const int cs = *w.cur_flip;
     const ManifoldSet cur = w.man[cs], prev = w.man[cs ^ 1];
@@ -437,8 +439,8 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
                 cur.body[pos] = pr[j];
                 cur.hdr[pos] = make_float4(sl.dx, sl.dy, friction, restitution);
                 cur.meta[pos] = make_int2(sl.count, color);
-                cur.geo[2 * pos] = make_float4(sl.p0x, sl.p0y, sl.d0, w.timestamp);
-                cur.geo[2 * pos + 1] = make_float4(sl.p1x, sl.p1y, sl.d1, two ? w.timestamp : 0.0f);
+                cur.geo[2 * pos] = make_float4(sl.p0x, sl.p0y, sl.d0, stamp);
+                cur.geo[2 * pos + 1] = make_float4(sl.p1x, sl.p1y, sl.d1, two ? stamp : 0.0f);
                 cur.imp[2 * pos] = make_float4(0.0f, lam_n0, 0.0f, lam_t0);
                 cur.imp[2 * pos + 1] = make_float4(0.0f, two ? lam_n1 : 0.0f, 0.0f, two ? lam_t1 : 0.0f);
                 cur.cid[2 * pos] = sl.id0;
@@ -465,6 +467,7 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
 template <int CO_ITEMS>
 __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned long long *status, unsigned int *ticket) {
     const unsigned int nprev = *w.prev_count;
+    const float stamp = w.scal->timestamp, dt = w.scal->dt;
     const unsigned int tile_size = NP_BLOCK * CO_ITEMS;
     const unsigned int ntiles = (nprev + tile_size - 1) / tile_size;
     const int cs = *w.cur_flip;
@@ -488,7 +491,7 @@ __global__ void __launch_bounds__(NP_BLOCK) k_carry_over(DevWorld w, unsigned lo
                 const int count = prev.meta[p].x;
                 bool keep = body[j].x >= 0 && body[j].y >= 0;
                 for (int c = 0; c < count && keep; ++c)
-                    if (w.timestamp - prev.geo[2 * p + c].w > w.dt) keep = false;
+                    if (stamp - prev.geo[2 * p + c].w > dt) keep = false;
                 if (keep) { keep_mask |= 1u << j; ++kept; q += (unsigned int) count; }
             }
         }
@@ -549,15 +552,17 @@ void fx_launch_rehash_prev(const DevWorld &w, const FxLaunchCtx &cx) {
     k_hash_build_prev<<<grid_for((long long) w.cap_manifolds, NP_BLOCK, cx.max_blocks), NP_BLOCK, 0, cx.stream>>>(w); ++g_fx_launches;
 }
 
+void fx_init_solver_attributes();
+// per-DEVICE opt-in shared memory sizes (a process may hold worlds on several GPUs)
+void fx_init_kernel_attributes() {
+    cudaFuncSetAttribute(k_narrowphase_tiled<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) NP2_SMEM(4));
+    fx_init_solver_attributes();
+}
+
 void fx_launch_narrowphase(const DevWorld &w, const FxLaunchCtx &cx) {
     cudaStream_t s = cx.stream;
     cudaMemsetAsync(w.touched, 0, w.cap_manifolds, s);
     if (w.narrow_mode == 0) {
-        static bool attr_set = false;
-        if (!attr_set) {
-            cudaFuncSetAttribute(k_narrowphase_tiled<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) NP2_SMEM(4));
-            attr_set = true;
-        }
         static const int force_items = [] { const char *e = std::getenv("FEROX_NP_ITEMS"); return e ? std::atoi(e) : 0; }();   // dev knob
         const int items = force_items ? force_items : (w.sol_mult == 1u ? 4 : 2);
         if (items == 4) k_narrowphase_tiled<4><<<grid_for((long long) w.cap_cand, NP2_BLOCK * 4, cx.max_blocks), NP2_BLOCK, NP2_SMEM(4), s>>>(w, cx.status[2], cx.tickets + 6);

@@ -93,7 +93,7 @@ struct StepCountersDev {
     unsigned int n_manifolds;    // M = hits + carried-over stale entries
     unsigned int n_contacts;     // Q
     unsigned int n_colors;
-    unsigned int overflow;       // bit 0: entries, 1: candidates, 2: manifolds, 3: colours, 4: key range
+    unsigned int overflow;       // bit 0: entries, 1: candidates, 2: manifolds, 3: colours, 4: key range (non-finite extent / sort passes)
     unsigned int sort_passes;
     int cell_min_x, cell_min_y, cell_max_x, cell_max_y;
     unsigned int grid_w, grid_h, key_bits, n_large;
@@ -112,14 +112,23 @@ static_assert(sizeof(GhostRow) == 96, "GhostRow layout");
 // message = 16-byte header {count, 0, 0, 0} + capacity rows (fixed size: no host round trip)
 #define FX_MSG_HEADER 16
 
+// Per-step scalars.  They live in device memory (DevWorld::scal) and not in the by-value kernel argument, so
+// that a captured CUDA graph of the step stays valid when the time step or the world clock changes
+// (frUpdateWorld moves the clock on every call): the host rewrites this block with a one-thread kernel ahead of
+// the (replayed) launch sequence whenever a value changed.
+struct StepScalars {
+    float gx, gy;
+    float timestamp;
+    float dt, inv_dt;
+    float pad[3];
+};
+
 struct DevWorld {
     int n;               // body rows the kernels sweep (owned bodies + ghost rows in strip mode)
     int n_owned;         // rows [0, n_owned) belong to this world; the rest are ghosts of neighbours
     int n_shapes;
     float cell, inv_cell;
-    float gx, gy;
-    float timestamp;
-    float dt, inv_dt;
+    const StepScalars *scal;   // gravity, world clock, dt (see above)
     int solver_mode;
     int sort_launch;     // radix-sort passes the host launches this step (k_plan refuses a world whose keys need more)
     int color_squeeze;   // how many of last step's top colours are re-coloured every step (0: never)
@@ -141,6 +150,7 @@ struct DevWorld {
     unsigned int *cell_cnt, *cell_off;   // per body entry count / exclusive offset
     unsigned int *large_list;            // bodies whose rectangle is expanded by a whole block
     unsigned int *keys[2], *vals[2];     // (cell key, packed body) entries, ping-pong for the sort
+    unsigned int *keys_hi[2];            // bits 32..63 of the cell keys; touched only in steps whose key needs them
     unsigned int *hist;                  // radix histograms [256][tiles]
     unsigned int cap_entries, cap_cand, cap_manifolds, cap_hash, cap_large;
     int2 *cand;          // candidate pairs (i < j)

@@ -93,10 +93,18 @@ struct frWorld_ {
     unsigned int d_gorder_cap = 0;
     int local_max_bodies = 0;        // 0: not eligible (some sub-world's bodies are not one short index range)
     int use_local = 1;
+    int force_large = 0;             // FEROX_FORCE_LARGE=1: the large-world kernel variants at any size (parity tests)
 
     HostMirror h;
     unsigned dirty = 0;
     bool device_newer = false;       // device state advanced past the host mirror
+    bool force_clear_pending = false;   // a completed step cleared the device accumulators; the mirror's are zeroed at the next pull
+    bool extent_unknown = false;     // a setter moved a body: launch every sort pass until a step has re-measured the key width
+    long long extent_mark_step = 0;  // w->steps when that happened
+    long long snapshot_step = -1;    // index of the step the pending / last snapshot belongs to
+    StepScalars *d_scal = nullptr;   // device block behind DevWorld::scal
+    StepScalars scal_dev{};          // what that block holds
+    bool scal_valid = false;
     unsigned stale = 0;              // while device_newer was being consumed piecewise: FX_DIRTY_* bits of mirror arrays not yet downloaded
     bool needs_sizing = true;        // run the sizing pre-pass before the next step
     bool device_ok = false;
@@ -164,6 +172,7 @@ struct frWorld_ {
     DevWorld last_key{};
     int graph_blocks = 0, last_blocks = 0;
     long long graph_launches = 0;
+    long long graph_replays = 0;     // steps served by cudaGraphLaunch (frxGetGraphReplays)
     bool graph_valid = false;
     int use_graph = 1;
 

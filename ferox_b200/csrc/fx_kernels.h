@@ -12,23 +12,27 @@ struct FxLaunchCtx {
     unsigned long long *status[4];  // 0 body prepass, 1 pair emission, 2 narrow phase, 3 carry-over
     size_t status_words[4];
     unsigned int *tickets;          // [16]
-    unsigned int *sort_hist;        // [4][256]
-    unsigned int *digit_status;     // [4][digit_status_stride]
+    unsigned int *sort_hist;        // [FX_SORT_MAX_PASSES][256]
+    unsigned int *digit_status;     // [FX_SORT_MAX_PASSES][digit_status_stride]
     size_t digit_status_stride;
     void *zero_base;                // one allocation backs everything above; cleared per step
     size_t zero_bytes;
+    size_t zero_fixed_bytes;        // everything ahead of digit_status (a step clears only the digit planes it sorts with)
 };
 
 // one LSD radix sort of (key, value) u32 pairs: ping-pong buffers, element count on the device
+#define FX_SORT_MAX_PASSES 8         // 8-bit digits of a key of up to 64 bits
 struct SortJob {
     unsigned int *keys[2], *vals[2];
+    unsigned int *keys_hi[2];         // high key words (nullptr: 32-bit keys)
+    const unsigned int *bits_dev;     // device-side key width; > 32 makes the high words live (nullptr: 32-bit keys)
     const unsigned int *n;
     const unsigned int *passes_dev;   // device-side pass count (nullptr: use `passes`)
     unsigned int passes;
-    unsigned int *ghist;              // [4][256], zeroed
-    unsigned int *dstatus;            // [4][dstatus_stride], zeroed
+    unsigned int *ghist;              // [passes][256], zeroed
+    unsigned int *dstatus;            // [passes][dstatus_stride], zeroed
     size_t dstatus_stride;
-    unsigned int *tickets;            // [4], zeroed
+    unsigned int *tickets;            // [passes], zeroed
 };
 
 // scratch of the serial-mode candidate ordering (allocated only when that mode is used)
@@ -53,7 +57,9 @@ struct SerialOrder {
 };
 
 void fx_launch_begin_step(const DevWorld &w, const FxLaunchCtx &cx);
-void fx_launch_integrate_velocity(const DevWorld &w, const FxLaunchCtx &cx);
+void fx_launch_integrate_velocity(const DevWorld &w, const FxLaunchCtx &cx, bool store_force = false);
+void fx_launch_set_scalars(StepScalars *dst, const StepScalars &v, cudaStream_t s);
+void fx_init_kernel_attributes();   // per DEVICE: opt-in shared memory sizes (call with the device current)
 void fx_launch_broadphase(const DevWorld &w, const FxLaunchCtx &cx, bool fuse_velocity);
 void fx_launch_lexsort_candidates(const DevWorld &w, const FxLaunchCtx &cx, const FxLexScratch &lex, int body_bits);
 void fx_launch_narrowphase(const DevWorld &w, const FxLaunchCtx &cx);

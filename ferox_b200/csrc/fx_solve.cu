@@ -61,7 +61,7 @@ __device__ __forceinline__ bool body_is_written(const DevWorld &w, int i) {
 
 // build the solver record of manifold m at slot s and apply its warm start (src/rigid_body.c:333-411)
 __device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const ManifoldSet &man, unsigned int m,
-                                                       unsigned int s, float4 *vel, int lo) {
+                                                       unsigned int s, float4 *vel, int lo, float inv_dt) {
     const int2 b = man.body[m];
     const float4 hdr = man.hdr[m];
     const int count = man.meta[m].x;
@@ -89,7 +89,7 @@ __device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const 
         const float4 im = man.imp[2 * m + c];
         ContactK k;
         contact_arms(k, v2(g.x, g.y), v2(pa4.x, pa4.y), v2(pb4.x, pb4.y));
-        k.bias = contact_bias(g.z, w.inv_dt);
+        k.bias = contact_bias(g.z, inv_dt);
         contact_masses(k, n, t, inv_ma, inv_mb, inv_ia, inv_ib);
         contact_warm_start(k, n, t, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
         w.sol.r[SOL_AT(w, s, c)] = make_float4(k.r1.x, k.r1.y, k.r2.x, k.r2.y);
@@ -171,6 +171,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     __shared__ unsigned int s_ncolors;
     const ManifoldSet man = w.man[*w.cur_flip];
     const unsigned int M = w.ctr->n_manifolds;
+    const float inv_dt = w.scal->inv_dt;
     const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     // per-colour loops: consecutive WARPS go to different blocks, so that a colour with fewer manifolds
     // than the grid has threads keeps a few warps busy on every SM instead of filling the first blocks
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     // ---- phase 3: solver records + warm start, one colour at a time
     for (unsigned int c = 0; c < s_ncolors; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
-        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, w.vel, 0);
+        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, w.vel, 0, inv_dt);
         grid.sync();
     }
     } else {
@@ -398,6 +399,7 @@ __global__ void k_solve_local(DevWorld w, int iterations, int max_bodies) {
     __shared__ unsigned int s_hist[FX_MAX_COLORS], s_off[FX_MAX_COLORS + 1], s_fill[FX_MAX_COLORS];
     __shared__ unsigned int s_left, s_ncolors;
     const ManifoldSet man = w.man[*w.cur_flip];
+    const float inv_dt = w.scal->inv_dt;
     const unsigned int tid = threadIdx.x, nth = blockDim.x;
     const bool batch = w.group != nullptr;
     const int ngroups = batch ? w.n_groups : 1;
@@ -507,7 +509,7 @@ __global__ void k_solve_local(DevWorld w, int iterations, int max_bodies) {
         const unsigned int ncolors = s_ncolors;
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
-            for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, svel, lo);
+            for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, svel, lo, inv_dt);
             __syncthreads();
         }
         for (int it = 0; it < iterations; ++it)
@@ -659,6 +661,7 @@ __global__ void k_solve_serial(DevWorld w, SerialOrder o, int iterations) {
     if (blockIdx.x != 0 || threadIdx.x != 0) return;
     const ManifoldSet man = w.man[*w.cur_flip];
     const unsigned int len = *o.r_len;
+    const float inv_dt = w.scal->inv_dt;
     for (int it = -1; it < iterations; ++it) {
         for (unsigned int r = 0; r < len; ++r) {
             int m = cache_lookup(w, o.r_key[r]);
@@ -690,7 +693,7 @@ __global__ void k_solve_serial(DevWorld w, SerialOrder o, int iterations) {
                     im.z = k.tmass;
                     contact_warm_start(k, n, t, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
                 } else {
-                    k.bias = contact_bias(g.z, w.inv_dt);
+                    k.bias = contact_bias(g.z, inv_dt);
                     k.nmass = im.x;
                     k.tmass = im.z;
                     contact_resolve(k, n, t, hdr.z, hdr.w, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
@@ -707,6 +710,11 @@ __global__ void k_solve_serial(DevWorld w, SerialOrder o, int iterations) {
 // ---------------------------------------------------------------------------------------------
 // launch surface
 // ---------------------------------------------------------------------------------------------
+// the shared-memory opt-in is a per-DEVICE function attribute: set when a world is created on a device
+void fx_init_solver_attributes() {
+    cudaFuncSetAttribute(k_solve_local, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_LOCAL_MAX_BODIES * 36);
+}
+
 int fx_query_coop_blocks(int device) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
@@ -757,12 +765,7 @@ void fx_launch_solve_local(const DevWorld &w, const FxLaunchCtx &cx, int iterati
         k_group_scan<<<1, 1024, 0, st>>>(w); ++g_fx_launches;
         k_group_scatter<<<g, 256, 0, st>>>(w); ++g_fx_launches;
     }
-    const size_t smem = (size_t) max_bodies * 36u;
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaFuncSetAttribute(k_solve_local, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (smem > 48 * 1024 ? smem : 48 * 1024));
-        attr = smem;
-    }
+    const size_t smem = (size_t) max_bodies * 36u;      // opt-in size: fx_init_solver_attributes (per device)
     const int threads = max_bodies <= 512 ? 256 : 1024;
     int blocks = batch ? w.n_groups : 1;
     const int cap = cx.num_sms * 16;

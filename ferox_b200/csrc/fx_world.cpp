@@ -110,19 +110,23 @@ static bool world_device_init(frWorld *w) {
     w->cx.max_blocks = sms * 8;
     w->cx.num_sms = sms;
     w->cx.coop_blocks = fx_query_coop_blocks(w->device);
-    fx_cuda_ok(cudaMalloc((void **) &w->d_snapshot, sizeof(StepCountersDev)), "cudaMalloc");
-    fx_cuda_ok(cudaMallocHost((void **) &w->h_snapshot, sizeof(StepCountersDev)), "cudaMallocHost");
-    std::memset(w->h_snapshot, 0, sizeof(StepCountersDev));
-    fx_cuda_ok(cudaEventCreateWithFlags(&w->snapshot_ready, cudaEventDisableTiming), "cudaEventCreate");
-    fx_cuda_ok(cudaMalloc((void **) &w->dw.ctr, sizeof(StepCountersDev)), "cudaMalloc");
-    fx_cuda_ok(cudaMalloc((void **) &w->dw.prev_count, 2 * sizeof(unsigned int)), "cudaMalloc");
-    fx_cuda_ok(cudaMalloc((void **) &w->dw.cur_flip, sizeof(int)), "cudaMalloc");
-    fx_cuda_ok(cudaMalloc((void **) &w->dw.color_off, (FX_MAX_COLORS + 1) * sizeof(unsigned int)), "cudaMalloc");
-    fx_cuda_ok(cudaMalloc((void **) &w->dw.color_scratch, 4 * FX_MAX_COLORS * sizeof(unsigned int)), "cudaMalloc");
+    fx_init_kernel_attributes();     // function attributes are per device
+    bool ok = fx_cuda_ok(cudaMalloc((void **) &w->d_snapshot, sizeof(StepCountersDev)), "cudaMalloc");
+    ok = fx_cuda_ok(cudaMallocHost((void **) &w->h_snapshot, sizeof(StepCountersDev)), "cudaMallocHost") && ok;
+    if (w->h_snapshot) std::memset(w->h_snapshot, 0, sizeof(StepCountersDev));
+    ok = fx_cuda_ok(cudaEventCreateWithFlags(&w->snapshot_ready, cudaEventDisableTiming), "cudaEventCreate") && ok;
+    ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.ctr, sizeof(StepCountersDev)), "cudaMalloc") && ok;
+    ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.prev_count, 2 * sizeof(unsigned int)), "cudaMalloc") && ok;
+    ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.cur_flip, sizeof(int)), "cudaMalloc") && ok;
+    ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.color_off, (FX_MAX_COLORS + 1) * sizeof(unsigned int)), "cudaMalloc") && ok;
+    ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.color_scratch, 4 * FX_MAX_COLORS * sizeof(unsigned int)), "cudaMalloc") && ok;
+    ok = fx_cuda_ok(cudaMalloc((void **) &w->d_scal, sizeof(StepScalars)), "cudaMalloc") && ok;
+    if (!ok) return false;
+    w->dw.scal = w->d_scal;
+    cudaMemsetAsync(w->d_scal, 0, sizeof(StepScalars), w->stream);
     cudaMemsetAsync(w->dw.ctr, 0, sizeof(StepCountersDev), w->stream);
     cudaMemsetAsync(w->dw.prev_count, 0, 2 * sizeof(unsigned int), w->stream);
     cudaMemsetAsync(w->dw.cur_flip, 0, sizeof(int), w->stream);
-    w->device_ok = (g_error == 0) || true;
     return fx_cuda_ok(cudaStreamSynchronize(w->stream), "world init");
 }
 
@@ -135,6 +139,9 @@ extern "C" frWorld *frCreateWorld(frVector2 gravity, float cellSize) {
     ring_resize(w, w->capacity);
     if (const char *g = std::getenv("FEROX_GRAPH")) w->use_graph = std::atoi(g);
     if (const char *g = std::getenv("FEROX_LOCAL_SOLVE")) w->use_local = std::atoi(g);
+    // parity knob (read per world): contact-major solver records, k_emit_pairs<4>, k_narrowphase_tiled<4>,
+    // k_carry_over<8> and k_solve_colored<2> -- the variants worlds of >= 400k manifolds run -- at any size
+    if (const char *g = std::getenv("FEROX_FORCE_LARGE")) { w->force_large = std::atoi(g); if (w->force_large) w->use_local = 0; }
     const char *mode = std::getenv("FEROX_SOLVER");
     if (mode && std::strcmp(mode, "serial") == 0) w->solver_mode = FRX_SOLVER_SERIAL;
     w->device_ok = world_device_init(w);
@@ -151,14 +158,14 @@ static void world_free_device(frWorld *w) {
     cudaFree(d.posrot); cudaFree(d.vel); cudaFree(d.mprop); cudaFree(d.force); cudaFree(d.aabb); cudaFree(d.angle);
     cudaFree(d.shape); cudaFree(d.uid); cudaFree(w->d_idx_of_uid); cudaFree(w->d_shapes);
     cudaFree(d.cell_cnt); cudaFree(d.cell_off); cudaFree(d.large_list);
-    cudaFree(d.keys[0]); cudaFree(d.keys[1]); cudaFree(d.vals[0]); cudaFree(d.vals[1]);
+    cudaFree(d.keys[0]); cudaFree(d.keys[1]); cudaFree(d.vals[0]); cudaFree(d.vals[1]); cudaFree(d.keys_hi[0]); cudaFree(d.keys_hi[1]);
     cudaFree(d.cand); cudaFree(d.cand_hit);
     free_manifold_set(d.man[0]); free_manifold_set(d.man[1]);
     cudaFree(d.touched); cudaFree(d.h_slot);
     cudaFree(d.sol.body); cudaFree(d.sol.nt); cudaFree(d.sol.mat); cudaFree(d.sol.count_src);
     cudaFree(d.sol.r); cudaFree(d.sol.u); cudaFree(d.sol.k); cudaFree(d.sol.lam);
     cudaFree(d.order); cudaFree(d.color_off); cudaFree(d.body_mask); cudaFree(d.body_dup); cudaFree(d.winner); cudaFree(d.cbody);
-    cudaFree(d.color_scratch); cudaFree(d.ctr); cudaFree(d.prev_count); cudaFree(d.cur_flip);
+    cudaFree(d.color_scratch); cudaFree(d.ctr); cudaFree(d.prev_count); cudaFree(d.cur_flip); cudaFree(w->d_scal);
     cudaFree(w->cx.zero_base);
     cudaFree(w->lex.keys[0]); cudaFree(w->lex.keys[1]); cudaFree(w->lex.vals[0]); cudaFree(w->lex.vals[1]);
     cudaFree(w->lex.tmp); cudaFree(w->lex.zero_base);
@@ -302,7 +309,10 @@ static bool ensure_body_capacity(frWorld *w, int need) {
 
 void fx_world_mark(frWorld *w, unsigned bits) {
     w->dirty |= bits;
-    if (bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) w->needs_sizing = true;
+    // A moved body can change the world's cell extent (hence the key width) but rarely the buffer sizes: no sizing
+    // pre-pass (a blocking extra broadphase) -- the next step launches every sort pass instead, the buffers keep their
+    // 2x head room, and a real overflow re-sizes the step after (read_snapshot).  Membership changes still re-size.
+    if (bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) { w->extent_unknown = true; w->extent_mark_step = w->steps; }
 }
 
 // bring the pinned host mirror up to date with the device (one bulk D2H per dynamic array)
@@ -313,8 +323,13 @@ void fx_world_pull_some(frWorld *w, unsigned want) {
     if (w->device_newer) {
         w->device_newer = false;
         w->stale = FX_DIRTY_POSROT | FX_DIRTY_ANGLE | FX_DIRTY_VEL | FX_DIRTY_AABB;
+    }
+    if (w->force_clear_pending) {
+        // only a COMPLETED step clears the accumulators (src/world.c:481-482); a pull from inside a pre-step
+        // handler must still see -- and keep -- what the user applied before frStepWorld
+        w->force_clear_pending = false;
         const size_t n0 = w->bodies.size();
-        if (n0) std::memset(w->h.force, 0, n0 * sizeof(float4));   // cleared by the step (src/world.c:481-482)
+        if (n0) std::memset(w->h.force, 0, n0 * sizeof(float4));
     }
     const unsigned get = w->stale & want;
     const size_t n = w->bodies.size();
@@ -485,7 +500,9 @@ static void attach_body(frWorld *w, frBody *b) {
     w->uid_dirty = true;
     HostMirror &h = w->h;
     h.posrot[i] = b->loc.posrot; h.angle[i] = b->loc.angle; h.vel[i] = b->loc.vel; h.mprop[i] = b->loc.mprop;
-    h.force[i] = b->loc.force; h.aabb[i] = b->loc.aabb;
+    // a body enters in the queue drain of frPostStepWorld, and the force clear that follows the drain covers it
+    // (src/world.c:450-482): whatever was applied to it while it was outside the world is gone by its first step
+    h.force[i] = make_float4(0.f, 0.f, 0.f, 0.f); h.aabb[i] = b->loc.aabb;
     h.shape[i] = make_int2(shape_slot(w, b->shape), b->shape ? (int) b->shape->type : 0);
     h.uid[i] = w->strip.uid_base + uid;
     h.group[i] = b->group;
@@ -553,15 +570,16 @@ static bool rebuild_zero_region(frWorld *w) {
     cx.status_words[0] = tiles_body; cx.status_words[1] = tiles_ent; cx.status_words[2] = tiles_cand; cx.status_words[3] = tiles_man;
     cx.digit_status_stride = sort_tiles * 256;
     size_t bytes = (tiles_body + tiles_ent + tiles_cand + tiles_man) * sizeof(unsigned long long) + 16 * sizeof(unsigned int) +
-                   4 * 256 * sizeof(unsigned int) + 4 * cx.digit_status_stride * sizeof(unsigned int);
+                   FX_SORT_MAX_PASSES * 256 * sizeof(unsigned int) + FX_SORT_MAX_PASSES * cx.digit_status_stride * sizeof(unsigned int);
     if (cx.zero_base) { cudaStreamSynchronize(w->stream); cudaFree(cx.zero_base); cx.zero_base = nullptr; }
     if (!fx_cuda_ok(cudaMalloc(&cx.zero_base, bytes), "cudaMalloc scratch")) return false;
     cx.zero_bytes = bytes;
     char *p = (char *) cx.zero_base;
     for (int k = 0; k < 4; ++k) { cx.status[k] = (unsigned long long *) p; p += cx.status_words[k] * sizeof(unsigned long long); }
     cx.tickets = (unsigned int *) p; p += 16 * sizeof(unsigned int);
-    cx.sort_hist = (unsigned int *) p; p += 4 * 256 * sizeof(unsigned int);
+    cx.sort_hist = (unsigned int *) p; p += FX_SORT_MAX_PASSES * 256 * sizeof(unsigned int);
     cx.digit_status = (unsigned int *) p;
+    cx.zero_fixed_bytes = (size_t) (p - (char *) cx.zero_base);
     return true;
 }
 
@@ -572,7 +590,8 @@ static bool ensure_work_capacity(frWorld *w, unsigned long long ent, unsigned lo
     if (ent > d.cap_entries) {
         unsigned int cap = (unsigned int) (ent < 0x7fffffffull ? ent : 0x7fffffffull);
         ok = ok && dev_realloc(d.keys[0], 0, cap, s, false) && dev_realloc(d.keys[1], 0, cap, s, false) &&
-             dev_realloc(d.vals[0], 0, cap, s, false) && dev_realloc(d.vals[1], 0, cap, s, false);
+             dev_realloc(d.vals[0], 0, cap, s, false) && dev_realloc(d.vals[1], 0, cap, s, false) &&
+             dev_realloc(d.keys_hi[0], 0, cap, s, false) && dev_realloc(d.keys_hi[1], 0, cap, s, false);
         d.cap_entries = cap;
         changed = true;
     }
@@ -654,23 +673,32 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.n = d.n_owned + (w->strip.enabled ? (int) w->strip.ghost_cap : 0);
     d.cell = w->cell;
     d.inv_cell = (w->cell > 0.0f) ? 1.0f / w->cell : 0.0f;     // src/broad_phase.c:62-63
-    d.gx = w->gravity.x;
-    d.gy = w->gravity.y;
-    d.timestamp = w->timestamp;
-    d.dt = dt;
-    d.inv_dt = 1.0f / dt;                                       // src/world.c:242
+    {
+        StepScalars sc{};
+        sc.gx = w->gravity.x;
+        sc.gy = w->gravity.y;
+        sc.timestamp = w->timestamp;
+        sc.dt = dt;
+        sc.inv_dt = 1.0f / dt;                                  // src/world.c:242
+        d.scal = w->d_scal;
+        if (!w->scal_valid || std::memcmp(&sc, &w->scal_dev, sizeof sc) != 0) {
+            fx_launch_set_scalars(w->d_scal, sc, w->stream);    // outside any captured graph: the graph stays valid
+            w->scal_dev = sc;
+            w->scal_valid = true;
+        }
+    }
     d.solver_mode = w->solver_mode;
     {
         // digit passes of the broadphase sort: all four until a step has told us the key width, then what that width
         // plus one bit needs (k_plan refuses a step whose keys need more than was launched)
         const unsigned int bits = w->last.key_bits;
-        d.sort_launch = (bits == 0u || w->needs_sizing) ? 4 : (int) ((bits + 1u + 7u) / 8u);
-        if (d.sort_launch > 4) d.sort_launch = 4;
+        d.sort_launch = (bits == 0u || w->needs_sizing || w->extent_unknown) ? FX_SORT_MAX_PASSES : (int) ((bits + 1u + 7u) / 8u);
+        if (d.sort_launch > FX_SORT_MAX_PASSES) d.sort_launch = FX_SORT_MAX_PASSES;
     }
     { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }
     {
         // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
-        const bool contact_major = w->manifold_hint >= 400000;
+        const bool contact_major = w->force_large || w->manifold_hint >= 400000;
         d.sol_stride = contact_major ? d.cap_manifolds : 1u;
         d.sol_mult = contact_major ? 1u : 2u;
     }
@@ -700,7 +728,8 @@ static void read_snapshot(frWorld *w, bool wait) {
     w->manifold_hint = w->last.n_manifolds;
     // bit 128 (a body outside its strip, static ownership) is a condition the caller reads from the counters, not lost work
     w->sticky_overflow |= w->last.overflow;
-    if (w->last.overflow & 16u) w->needs_sizing = true;      // next step: all four sort passes, buffers re-measured
+    if (w->last.overflow & (1u | 2u | 4u | 16u)) w->needs_sizing = true;      // next step: every sort pass, buffers re-measured
+    if (w->extent_unknown && w->snapshot_step >= w->extent_mark_step) w->extent_unknown = false;   // key width re-measured since
     if (w->last.overflow & ~128u) {
         char buf[260];
         std::snprintf(buf, sizeof buf,
@@ -725,7 +754,7 @@ static bool sizing_prepass(frWorld *w, float dt) {
         if (!fx_cuda_ok(cudaStreamSynchronize(w->stream), "sizing pre-pass")) return false;
         c = *w->h_snapshot;
         if (c.overflow & 16u) {
-            fx_set_error(3, "world extent exceeds 2^32 broadphase cells (or a body covers > 2^24 cells): enlarge cellSize");
+            fx_set_error(3, "non-finite world extent (> 2^62 broadphase cells), or a body covers > 2^24 cells: enlarge cellSize");
             return false;
         }
         // n_entries / n_cand are clamped to the capacity on overflow: grow and measure again
@@ -791,20 +820,33 @@ static void launch_step_sequence(frWorld *w, bool collide, bool has_handler, boo
     if (serial) fx_launch_serial_order(d, w->cx, w->so);
     prof_mark(w);
     if (has_handler) {
-        w->device_newer = true;
+        // The pre-step sweep runs BEFORE gravity and the velocity integration (src/world.c:209-220): forces applied
+        // before frStepWorld are still in the mirror's accumulators (only a completed step clears them) and forces
+        // the handler applies are uploaded with them.
         if (w->handler.preStep) run_handler(w, w->handler.preStep);      // src/world.c:209-214
         world_push(w);                                                    // setters called by the handler
-        fx_launch_integrate_velocity(d, w->cx);                           // src/world.c:216-220
+        fx_launch_integrate_velocity(d, w->cx, true);                     // src/world.c:216-220; accumulators keep the gravity term
+        if (w->handler.postStep && !w->bodies.empty())                    // frGetBodyForce inside postStep: what the reference holds then
+            cudaMemcpyAsync(w->h.force, d.force, w->bodies.size() * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
     }
     if (serial) fx_launch_solve_serial_with(d, w->cx, w->so, FR_WORLD_ITERATION_COUNT);
     else if (w->use_local && w->local_max_bodies > 0) fx_launch_solve_local(d, w->cx, FR_WORLD_ITERATION_COUNT, w->local_max_bodies);
     else fx_launch_solve_colored(d, w->cx, FR_WORLD_ITERATION_COUNT, hint);
+    if (!fx_cuda_ok(cudaGetLastError(), "solver launch")) return;        // no contact solve: do not integrate positions on top of it
     prof_mark(w);
     fx_launch_integrate_position(d, w->cx);
     prof_mark(w);
     w->device_newer = true;
-    if (has_handler && w->handler.postStep) run_handler(w, w->handler.postStep);   // src/world.c:254-259
-    if (has_handler) world_push(w);
+    if (has_handler) {
+        if (w->handler.postStep) run_handler(w, w->handler.postStep);    // src/world.c:254-259
+        // frPostStepWorld clears every accumulator AFTER the sweep (src/world.c:481-482): forces applied inside a
+        // post-step handler are wiped with the rest (the device copy was cleared by the position kernel)
+        w->dirty &= ~(unsigned) FX_DIRTY_FORCE;
+        if (!w->bodies.empty()) std::memset(w->h.force, 0, w->bodies.size() * sizeof(float4));
+        world_push(w);
+    } else {
+        w->force_clear_pending = true;
+    }
     fx_launch_finish_step(d, w->cx, w->d_snapshot);
     cudaMemcpyAsync(w->h_snapshot, w->d_snapshot, sizeof(StepCountersDev), cudaMemcpyDeviceToHost, w->stream);
 }
@@ -833,7 +875,8 @@ static void step_once(frWorld *w, float dt) {
     world_push(w);
     fill_dev_params(w, dt);
 
-    const long long hint = w->manifold_hint > (long long) w->bodies.size() ? w->manifold_hint : (long long) w->bodies.size();
+    long long hint = w->manifold_hint > (long long) w->bodies.size() ? w->manifold_hint : (long long) w->bodies.size();
+    if (w->force_large && hint < 400000) hint = 400000;
     const int coop_blocks = fx_solve_colored_blocks(w->cx, hint);
     // ---- fast path: replay the captured launch sequence ----
     const bool graphable = w->use_graph && !has_handler && !serial && !w->profiling;
@@ -870,12 +913,15 @@ static void step_once(frWorld *w, float dt) {
     if (graphable && w->graph_valid) {
         cudaGraphLaunch(w->graph_exec, w->stream);
         g_fx_launches += w->graph_launches;
+        w->graph_replays++;
         w->device_newer = true;
+        w->force_clear_pending = true;
     } else {
         launch_step_sequence(w, collide, has_handler, serial, hint);
     }
     cudaEventRecord(w->snapshot_ready, w->stream);
     w->snapshot_pending = true;
+    w->snapshot_step = w->steps;
     w->steps++;
     fx_cuda_ok(cudaGetLastError(), "step launch");
 
@@ -952,6 +998,7 @@ extern "C" float frxEventElapsedMs(frWorld *w, int from, int to) {
     return ms;
 }
 extern "C" long long frxGetLaunchCount(void) { return g_fx_launches; }
+extern "C" long long frxGetGraphReplays(const frWorld *w) { return w ? w->graph_replays : 0; }
 extern "C" void frxProfilerRange(int start) { if (start) cudaProfilerStart(); else cudaProfilerStop(); }
 
 // n steps, each bracketed by its own pair of CUDA events on the world's stream; when flushL2 != 0 a
@@ -1291,6 +1338,7 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
                                    st.send_full, st.ghost_cap, 0.5f, 0);          // restore the true inverse masses
         fx_launch_integrate_position(d, w->cx);
         w->device_newer = true;
+        w->force_clear_pending = true;
         fx_launch_finish_step(d, w->cx, w->d_snapshot);
         cudaMemcpyAsync(w->h_snapshot, w->d_snapshot, sizeof(StepCountersDev), cudaMemcpyDeviceToHost, w->stream);
         cudaEventRecord(w->snapshot_ready, w->stream);

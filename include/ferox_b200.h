@@ -333,6 +333,9 @@ int frxGetStageTimes(frWorld *w, double *outMs5);
 void frxRecordEvent(frWorld *w, int slot);
 float frxEventElapsedMs(frWorld *w, int fromSlot, int toSlot);
 long long frxGetLaunchCount(void);
+/* steps of this world that were served by replaying the captured CUDA graph of the launch sequence (the graph
+   survives changes of dt and of the world clock: frUpdateWorld replays it call after call) */
+long long frxGetGraphReplays(const frWorld *w);
 /* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture a span */
 void frxProfilerRange(int start);
 /* n frStepWorld calls, each bracketed by its own CUDA-event pair on the world's stream; with flushL2

@@ -47,6 +47,8 @@ def lib():
         L.orc_set_bodies.argtypes = [C.c_void_p, i32p, i32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p, f32p]
         L.orc_set_forces.argtypes = [C.c_void_p, f32p, f32p]
         L.orc_set_timestamp.argtypes = [C.c_void_p, C.c_float]
+        L.orc_set_solve_order.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong]
+        L.orc_last_colors.argtypes = [C.c_void_p]
         L.orc_step.argtypes = [C.c_void_p, C.c_float]
         L.orc_get_state.argtypes = [C.c_void_p, f32p, f32p, f32p, f32p, f32p, f32p]
         L.orc_candidate_count.argtypes = [C.c_void_p]
@@ -120,6 +122,11 @@ class OracleWorld:
     def set_forces(self, force, torque):
         self.L.orc_set_forces(self.h, np.ascontiguousarray(force, np.float32).reshape(-1),
                               np.ascontiguousarray(torque, np.float32))
+
+    def set_solve_order(self, mode, seed=1):
+        """0: reference (array) order; 1: greedy colour-major; 2: random permutation per step.  1 and 2 are NOT the
+        reference: they measure how much a pure re-ordering of the sweeps moves the statistics (App. A.13)."""
+        self.L.orc_set_solve_order(self.h, {"reference": 0, "colored": 1, "random": 2}.get(mode, mode), seed)
 
     def set_timestamp(self, ts):
         self.L.orc_set_timestamp(self.h, ts)

@@ -95,6 +95,17 @@ typedef struct orc_world {
     int n_cand, cap_cand;
     /* counters: K cell entries, C candidates, M manifolds, Q contacts */
     long long K, Cn, M, Q;
+    /* Gauss-Seidel visiting order of the solver loops (src/world.c:237-249).  0: the reference's (cache array
+       order).  1: greedy colour-major (lowest colour free on both bodies the solver writes, taken in array
+       order; then colour by colour).  2: a fresh seeded random permutation every step.  Modes 1 and 2 are NOT
+       the reference: they exist so that tests can MEASURE, on the reference's own arithmetic, how much a pure
+       re-ordering of the same sweeps moves the statistics -- the yardstick for the
+       tolerance of the graph-coloured GPU solver. */
+    int solve_order;
+    uint64_t order_seed;
+    int *perm;
+    int cap_perm;
+    int last_colors;
 } orc_world;
 
 /* ---------------------------------------------------------------------------------------------- */
@@ -693,7 +704,7 @@ void orc_destroy(orc_world *w) {
     free(w->shapes); free(w->type); free(w->shape); free(w->tx); free(w->vel); free(w->force);
     free(w->omega); free(w->torque); free(w->mass); free(w->inv_mass); free(w->inertia);
     free(w->inv_inertia); free(w->gravity_scale); free(w->aabb); free(w->entries);
-    free(w->ht_key); free(w->ht_val); free(w->cand); free(w);
+    free(w->ht_key); free(w->ht_val); free(w->cand); free(w->perm); free(w);
 }
 
 void orc_set_shape(orc_world *w, int s, int type, float radius, int nv, const float *verts,
@@ -726,6 +737,45 @@ void orc_set_forces(orc_world *w, const float *force, const float *torque) {
 }
 
 void orc_set_timestamp(orc_world *w, float ts) { w->timestamp = ts; }
+void orc_set_solve_order(orc_world *w, int mode, unsigned long long seed) { w->solve_order = mode; w->order_seed = seed; }
+int orc_last_colors(const orc_world *w) { return w->last_colors; }
+
+/* visiting order of the solver loops for solve_order != 0 (NULL: array order, the reference's) */
+static const int *solve_permutation(orc_world *w) {
+    const int m = w->n_entries;
+    if (w->solve_order == 0 || m == 0) return NULL;
+    if (w->cap_perm < m) { w->cap_perm = m + m / 2 + 16; w->perm = realloc(w->perm, sizeof(int) * (size_t) w->cap_perm); }
+    if (w->solve_order == 2) {
+        for (int j = 0; j < m; j++) w->perm[j] = j;
+        for (int j = m - 1; j > 0; j--) {                                  /* Fisher-Yates on splitmix64 */
+            uint64_t z = (w->order_seed += 0x9E3779B97F4A7C15ull);
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull; z ^= z >> 31;
+            int k = (int) (z % (uint64_t) (j + 1)), t = w->perm[j];
+            w->perm[j] = w->perm[k]; w->perm[k] = t;
+        }
+        return w->perm;
+    }
+    /* greedy colouring: only bodies the solver writes (invMass > 0 or invInertia > 0) constrain it (App. A.13) */
+    uint64_t *used = calloc((size_t) w->n, sizeof(uint64_t));
+    int *col = malloc(sizeof(int) * (size_t) m), cnt[65] = { 0 }, ncol = 0;
+    for (int j = 0; j < m; j++) {
+        const int a = w->entries[j].a, b = w->entries[j].b;
+        const int wa = w->inv_mass[a] > 0.0f || w->inv_inertia[a] > 0.0f, wb = w->inv_mass[b] > 0.0f || w->inv_inertia[b] > 0.0f;
+        uint64_t u = (wa ? used[a] : 0) | (wb ? used[b] : 0);
+        int c = 0;
+        while (c < 63 && ((u >> c) & 1)) c++;
+        col[j] = c;
+        if (wa) used[a] |= 1ull << c;
+        if (wb) used[b] |= 1ull << c;
+        cnt[c + 1]++;
+        if (c + 1 > ncol) ncol = c + 1;
+    }
+    for (int c = 0; c < 64; c++) cnt[c + 1] += cnt[c];
+    for (int j = 0; j < m; j++) w->perm[cnt[col[j]]++] = j;
+    w->last_colors = ncol;
+    free(col); free(used);
+    return w->perm;
+}
 
 /* frStepWorld, src/world.c:204-262 (no collision handler; the world is fixed-size here) */
 void orc_step(orc_world *w, float dt) {
@@ -748,10 +798,11 @@ void orc_step(orc_world *w, float dt) {
                 if (w->timestamp - value->contacts[k].timestamp > dt) { cache_del(w, a, b); break; }
         }
     }
-    for (int j = 0; j < w->n_entries; j++) warm_start(w, &w->entries[j]); /* :237-240 */
+    const int *perm = solve_permutation(w);
+    for (int j = 0; j < w->n_entries; j++) warm_start(w, &w->entries[perm ? perm[j] : j]); /* :237-240 */
     float inv_dt = 1.0f / dt;
     for (int it = 0; it < ORC_ITERATIONS; it++)                           /* :242-249 */
-        for (int j = 0; j < w->n_entries; j++) resolve(w, &w->entries[j], inv_dt);
+        for (int j = 0; j < w->n_entries; j++) resolve(w, &w->entries[perm ? perm[j] : j], inv_dt);
     for (int i = 0; i < w->n; i++) integrate_position(w, i, dt);          /* :251-252 */
     for (int i = 0; i < w->n; i++) { w->force[i].x = w->force[i].y = w->torque[i] = 0.0f; } /* :481-482 */
     w->M = w->n_entries; w->Q = 0;

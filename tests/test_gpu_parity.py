@@ -275,20 +275,27 @@ def test_colored_mode_is_exact_when_manifolds_are_independent(gpu):
 
 def test_colored_mode_single_step_within_ordering_tolerance(gpu):
     """From bit-identical state (reached in reference-order mode) one coloured step differs from the
-    reference-order step only by the Gauss-Seidel ordering effect.  SURVEY App. A.13 measured that
-    effect on the reference itself: rms |dv| 0.03-0.09, max 0.2-0.9 units/s.  Tolerance stated here:
-    rms |dv| <= 0.25, max |dv| <= 1.5 units/s, max |dx| <= 0.03 units; pair set and contact
-    geometry stay bit-exact (they are computed before the solver runs)."""
+    reference-order step only by the Gauss-Seidel ordering effect.  The yardstick is MEASURED here, on the
+    reference's own arithmetic: a second oracle takes the same step with its sweeps re-ordered colour-major
+    (oracle/step_oracle.c `solve_order`: same contacts, same sweeps, another visiting order -- what SURVEY App. A.13
+    probed), a third in a random order.  The GPU step must stay within 1.5x of the larger re-ordering effect (rms and max |dv|, max |dx|); pair set
+    and contact geometry stay bit-exact (they are computed before the solver runs)."""
     L = gpu
     spec = scenes.mixed_pile(2000, width=70.0)
     sc = make_world(L, spec, fb.SOLVER_SERIAL)
     ow = orc.OracleWorld.from_scene(sc)
+    ow2, ow3 = orc.OracleWorld.from_scene(sc), orc.OracleWorld.from_scene(sc)
     L.frxStepWorldN(sc.world, DT, 300)
-    ow.step(300)
+    for o in (ow, ow2, ow3):
+        o.step(300)
     assert_states_equal(fb.body_states(L, sc.world), ow.state(), "serial prefix")
     L.frxSetWorldSolverMode(sc.world, fb.SOLVER_COLORED)
     L.frStepWorld(sc.world, DT)
     ow.step(1)
+    ow2.set_solve_order("colored")
+    ow2.step(1)
+    ow3.set_solve_order("random", 11)
+    ow3.step(1)
     got, want = fb.body_states(L, sc.world), ow.state()
     assert sorted(map(tuple, fb.candidate_pairs(L, sc.world))) == sorted(map(tuple, ow.candidates()))
     m, oc = fb.manifolds(L, sc.world), ow.cache()
@@ -299,43 +306,63 @@ def test_colored_mode_single_step_within_ordering_tolerance(gpu):
         assert m[f].tobytes() == oc[f].tobytes(), f
     for f in ("id", "depth", "point"):
         assert np.ascontiguousarray(m["contacts"][f]).tobytes() == np.ascontiguousarray(oc["contacts"][f]).tobytes(), f
-    dv = np.linalg.norm(got["vel"] - want["vel"], axis=1)
-    dx = np.linalg.norm(got["pos"] - want["pos"], axis=1)
-    assert np.sqrt((dv ** 2).mean()) <= 0.25 and dv.max() <= 1.5 and dx.max() <= 0.03, (np.sqrt((dv ** 2).mean()), dv.max(), dx.max())
+
+    def effect(a):
+        dv = np.linalg.norm(a["vel"] - want["vel"], axis=1)
+        dx = np.linalg.norm(a["pos"] - want["pos"], axis=1)
+        return float(np.sqrt((dv ** 2).mean())), float(dv.max()), float(dx.max())
+    (g_rms, g_max, g_dx) = effect(got)
+    o_rms, o_max, o_dx = (max(x) for x in zip(effect(ow2.state()), effect(ow3.state())))   # colour-major and random re-orderings
+    assert o_rms > 0.0, "the yardstick step did not differ from the reference order at all"
+    assert g_rms <= 1.5 * o_rms and g_max <= 1.5 * o_max + 0.05 and g_dx <= 1.5 * o_dx + 1e-3, \
+        ("gpu", g_rms, g_max, g_dx, "re-ordered reference", o_rms, o_max, o_dx)
     c = fb.step_counters(L, sc.world)
     assert 2 <= c["colors"] <= 24
-    sc.release(); ow.close()
+    sc.release(); ow.close(); ow2.close(); ow3.close()
 
 
 def test_colored_mode_long_run_statistics(gpu):
-    """1,000 steps: potential energy, mean penetration depth and contact counts of the coloured
-    solver agree with the reference-order oracle within 1 % / 3 % / 5 % (means of the last 200 steps; the
-    contact count of a still-creeping pile fluctuates by a few per cent between any two orderings).
-    Residual kinetic energy is chaotic in the reference itself (App. A.13) and is only bounded."""
+    """1,000 steps (means of the last 200).  north_star asks for energy and penetration statistics within 1 %.  How
+    far a pure RE-ORDERING of the reference's own sweeps moves each statistic is measured in this test: two more
+    oracles run the same scene colour-major and in a fresh random order every step (oracle/step_oracle.c
+    `solve_order`).  [measured, CPU] on this scene the re-ordered reference itself differs from the reference by
+    ~0.3-0.5 % in potential energy, 1.5-2 % in mean penetration, 2-2.5 % in contact count and 25-50 % in residual
+    kinetic energy (the chaotic jitter of a "resting" pile, App. A.13).  Asserted: potential energy within 1 %
+    outright; mean penetration and contact count within max(1 %, 1.5 x the largest re-ordering spread measured
+    here); kinetic energy within 3 x the largest re-ordered value."""
     L = gpu
     spec = scenes.mixed_pile(2500, width=80.0)
     sc = make_world(L, spec, fb.SOLVER_COLORED)
-    ow = orc.OracleWorld.from_scene(sc)
-    n = spec.n
+    ows = []
+    for mode in ("reference", "colored", "random"):
+        ow = orc.OracleWorld.from_scene(sc)
+        ow.set_solve_order(mode, 7)
+        ows.append(ow)
     masses = np.array([L.frGetBodyMass(b) for b in sc.bodies], np.float64)
-    pe, pen, cnt, ke = [[], []], [[], []], [[], []], [[], []]
+    runs = [dict(pe=[], pen=[], cnt=[], ke=[]) for _ in range(4)]       # gpu, reference order, colour-major, random
     for s in range(1000):
         L.frStepWorld(sc.world, DT)
-        ow.step(1)
+        for ow in ows:
+            ow.step(1)
         if s >= 800:
-            for j, (st, cache) in enumerate(((fb.body_states(L, sc.world), fb.manifolds(L, sc.world)), (ow.state(), ow.cache()))):
-                pe[j].append(-(masses * 9.8 * st["pos"][:, 1]).sum())
-                ke[j].append(0.5 * (masses * (st["vel"].astype(np.float64) ** 2).sum(1)).sum())
+            views = [(fb.body_states(L, sc.world), fb.manifolds(L, sc.world))] + [(ow.state(), ow.cache()) for ow in ows]
+            for r, (st, cache) in zip(runs, views):
+                r["pe"].append(-(masses * 9.8 * st["pos"][:, 1]).sum())
+                r["ke"].append(0.5 * (masses * (st["vel"].astype(np.float64) ** 2).sum(1)).sum())
                 d = np.concatenate([cache["contacts"]["depth"][:, 0], cache["contacts"]["depth"][cache["count"] > 1, 1]])
-                pen[j].append(d.mean())
-                cnt[j].append(int(cache["count"].sum()))
+                r["pen"].append(d.mean())
+                r["cnt"].append(int(cache["count"].sum()))
     fb.check_error(L)
-    rel = lambda a: abs(np.mean(a[0]) - np.mean(a[1])) / abs(np.mean(a[1]))
-    assert rel(pe) <= 0.01, ("potential energy", rel(pe))
-    assert rel(pen) <= 0.03, ("mean penetration", rel(pen))
-    assert rel(cnt) <= 0.05, ("contact count", rel(cnt))
-    assert np.mean(ke[0]) <= 3.0 * np.mean(ke[1]) + 1.0
-    sc.release(); ow.close()
+    mean = lambda j, k: float(np.mean(runs[j][k]))
+    rel = lambda j, k: abs(mean(j, k) - mean(1, k)) / abs(mean(1, k))
+    spread = {k: max(rel(2, k), rel(3, k)) for k in ("pe", "pen", "cnt")}
+    assert rel(0, "pe") <= 0.01, ("potential energy", rel(0, "pe"), spread)
+    assert rel(0, "pen") <= max(0.01, 1.5 * spread["pen"]), ("mean penetration", rel(0, "pen"), spread)
+    assert rel(0, "cnt") <= max(0.01, 1.5 * spread["cnt"]), ("contact count", rel(0, "cnt"), spread)
+    assert mean(0, "ke") <= 3.0 * max(mean(1, "ke"), mean(2, "ke"), mean(3, "ke")) + 1.0
+    sc.release()
+    for ow in ows:
+        ow.close()
 
 
 def test_colored_mode_is_deterministic(gpu):
@@ -725,3 +752,99 @@ def test_update_world_accumulator_matches_reference_with_a_fake_clock(gpu, ref):
         out.append([l for l in r.stdout.splitlines() if l.startswith("HASH")][-1])
     assert out[0] == out[1], out
     assert int(out[0].split()[2]) == 303          # the bodies did enter the world (a call ran at least one step)
+
+
+def test_update_world_replays_the_captured_graph_across_calls(gpu):
+    """frUpdateWorld moves the world clock on every call (src/world.c:274,281).  The per-step scalars (clock, dt,
+    gravity) live in a device block, not in the captured kernel arguments, so the CUDA graph of the launch
+    sequence survives: under the same deterministic clock as above nearly every step of 120 calls is a replay."""
+    import os, subprocess, sys, tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = os.path.join(tempfile.mkdtemp(), "libfake_clock.so")
+    subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(root, "tests", "c", "fake_clock.c")])
+    code = ("import ferox_b200 as fb\n"
+            "from ferox_b200 import scenes\n"
+            "L = fb.lib(); L.frxSetDevice(0)\n"
+            "sc = scenes.Scene(L, scenes.mixed_pile(6000, width=150.0), prime=False)\n"
+            "for k in range(120): L.frUpdateWorld(sc.world, scenes.DT)\n"
+            "c = fb.step_counters(L, sc.world); fb.check_error(L)\n"
+            "print('GRAPH', c['steps'], L.frxGetGraphReplays(sc.world), c['manifolds'])\n")
+    env = dict(os.environ, LD_PRELOAD=so, PYTHONPATH=root)
+    env.pop("FEROX_GRAPH", None)
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    steps, replays, manifolds = (int(x) for x in [l for l in r.stdout.splitlines() if l.startswith("GRAPH")][-1].split()[1:])
+    assert steps >= 100 and manifolds > 0
+    # the first steps size the buffers and wait for two identical parameter sets; growth re-captures a few times
+    assert replays >= steps - 40, (steps, replays)
+
+
+def test_mutating_handlers_forces_and_membership_match_reference(gpu, ref):
+    """The SAME collision handlers on the unmodified reference and on the product (reference-order mode), doing
+    what real programs do (examples/src/cows.c:375-393, melon.c:283-311): pre-step edits that must persist or
+    take effect (count = 0 disables a manifold for the step, a friction edit sticks through the cache,
+    src/world.c:209-214,366-367), forces applied before the step / inside the pre-step sweep (they act,
+    :216-220) / inside the post-step sweep (they are wiped, :481-482), frGetBodyForce read in both sweeps, and
+    bodies removed and added from inside a callback (:450-479).  The callback logs (order, pairs, counts, depths,
+    impulses, forces seen) and every body state must agree bit for bit, step by step."""
+    L = gpu
+    base = scenes.mixed_pile(150, width=26.0)
+    spec = scenes.SceneSpec(name="handlers", cell=base.cell, shapes=list(base.shapes))
+    far = np.array([[5.0, -300.0], [9.0, -300.0]], np.float32)        # two bodies that never touch anything
+    scenes._finish(spec, np.concatenate([base.body_type, [capi.BODY_DYNAMIC] * 2]), np.concatenate([base.body_shape, [2, 2]]),
+                   np.concatenate([base.pos, far]), np.concatenate([base.angle, [0.0, 0.0]]))
+    runs = []
+    for lib in (ref, L):
+        sc = scenes.Scene(lib, spec, prime=False)
+        if lib is L:
+            lib.frxSetWorldSolverMode(sc.world, fb.SOLVER_SERIAL)
+        lib.frStepWorld(sc.world, DT)
+        spare = lib.frCreateBodyFromShape(capi.BODY_DYNAMIC, capi.Vector2(13.0, -250.0), sc.shapes[2])
+        sc.bodies.append(spare); sc.index_of[spare] = len(sc.bodies) - 1
+        log, state = [], {"step": 0}
+
+        def pre(key, value, lib=lib, sc=sc, log=log, state=state):
+            c = value.contents
+            a, b = sc.index_of[key.first], sc.index_of[key.second]
+            f = lib.frGetBodyForce(key.second)
+            log.append(("pre", state["step"], a, b, c.count, c.friction, c.contacts[0].depth, c.contacts[0].cache.normalScalar, f.x, f.y))
+            if (a + b) % 7 == 0:
+                c.count = 0
+            if (a + b) % 5 == 0:
+                c.friction = 0.125
+            if (a + b) % 11 == 0:
+                lib.frApplyForceToBody(key.second, lib.frGetBodyPosition(key.second), capi.Vector2(3.0, -2.0))
+
+        def post(key, value, lib=lib, sc=sc, log=log, state=state):
+            c = value.contents
+            a, b = sc.index_of[key.first], sc.index_of[key.second]
+            f = lib.frGetBodyForce(key.second)
+            log.append(("post", state["step"], a, b, c.count, c.friction, c.contacts[0].cache.normalScalar,
+                        c.contacts[0].cache.tangentScalar, c.contacts[0].cache.normalMass, f.x, f.y, lib.frGetBodyTorque(key.second)))
+            lib.frApplyForceToBody(key.first, lib.frGetBodyPosition(key.first), capi.Vector2(50.0, 0.0))     # wiped by the post-step
+            if state["step"] == 20 and "removed" not in state:
+                state["removed"] = lib.frRemoveBodyFromWorld(sc.world, sc.bodies[-2])
+            if state["step"] == 30 and "added" not in state:
+                state["added"] = lib.frAddBodyToWorld(sc.world, sc.bodies[-1])
+
+        h = capi.CollisionHandler(capi.CollisionEventFunc(pre), capi.CollisionEventFunc(post))
+        lib.frSetWorldCollisionHandler(sc.world, h)
+        snaps = []
+        for s in range(60):
+            state["step"] = s
+            if s % 9 == 4:
+                lib.frApplyForceToBody(sc.bodies[40], lib.frGetBodyPosition(sc.bodies[40]), capi.Vector2(-6.0, 1.5))
+            lib.frStepWorld(sc.world, DT)
+            members = [sc.index_of[lib.frGetBodyInWorld(sc.world, i)] for i in range(lib.frGetBodyCountInWorld(sc.world))]
+            snaps.append((members, scenes.snapshot(lib, sc.bodies)))
+        runs.append((log, snaps, h))
+    fb.check_error(L)
+    (rlog, rsnaps, _), (glog, gsnaps, _) = runs
+    assert len(rlog) == len(glog) and len(rlog) > 2000
+    f32 = lambda t: tuple(np.float32(x).tobytes() if isinstance(x, float) else x for x in t)
+    for k, (x, y) in enumerate(zip(rlog, glog)):
+        assert f32(x) == f32(y), (k, x, y)
+    for s, ((rm, rst), (gm, gst)) in enumerate(zip(rsnaps, gsnaps)):
+        assert rm == gm, "membership at step %d" % s
+        assert_states_equal(rst, gst, "step %d" % s)
+    assert any(e[0] == "pre" and e[4] > 0 and abs(e[5] - 0.125) < 1e-7 for e in rlog[len(rlog) // 2:])   # the friction edit stuck
