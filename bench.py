@@ -17,6 +17,17 @@ One JSON line on rank 0, see the contract in the task description:
              (964 B/manifold + 376 B/contact) / its mean device time, against MEASURED_PEAKS.json
   cpu_baseline  oracle/step_oracle.c (a port; 1 core) on the same settled state, a few steps
 
+Sub-records in the same line (driver-witnessed, each a bounded run of the same build in the same process):
+  config1   BASELINE configs[0]: 1,024 boxes on static ground, 1 priming + 600 timed steps
+  config3   BASELINE configs[2]: 1,048,576 uniform circles, 512 x 2,048 column, right wall removed at t = 0, on a
+            16,384-unit floor -- the 600 steps of the collapse, timed; Hz, overflow, per-kernel roofline
+  config4   BASELINE configs[3]: 4,096 independent worlds x 256 bodies.  N = 1: one batch on the GPU + the CPU
+            baseline (unmodified reference, one world per process on every host core).  N > 1: the worlds
+            sharded round-robin over the ranks (strong scaling) AND 4,096 worlds on every rank (weak scaling)
+  config5   (N > 1) BASELINE configs[4] scaled to the box: ONE pile of N x 1,048,576 bodies cut into N strips, one per
+            rank, ghost bodies and per-stage velocity changes exchanged with the library's own NCCL communicator
+`--skip-sub` leaves them out (profiling runs).
+
 `--impl reference` times the UNMODIFIED reference (oracle/_ref/libferox_ref_70000.so, compiled from
 /root/reference by oracle/Makefile) on the host cores: one world per process on every core.
 """
@@ -48,6 +59,8 @@ def parse_args():
     ap.add_argument("--bodies", type=int, default=65536)
     ap.add_argument("--settle", type=int, default=600)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-sub", action="store_true", help="no config1/3/4/5 sub-records (profiling runs)")
+    ap.add_argument("--sub-steps", type=int, default=200, help="timed steps of the config4 / config5 sub-records")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
                     help="config2 (default, the headline): one 65,536-body mixed pile per GPU; config3: one 1M-circle column "
                          "collapse per GPU; config4: 4,096 independent 256-body worlds batched into one launch set and "
@@ -116,7 +129,7 @@ def build_config4_batch(L, n_worlds, rank, world_size):
 # clocks (B200_PROFILING.md recipe): sampled DURING the timed region
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -132,7 +145,8 @@ class ClockSampler:
         except OSError:
             self.proc = None
 
-    def stop(self):
+    def stop(self, window=None):
+        """window = (t0, t1) in time.time() seconds: only the samples taken inside it count (the timed region)."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -141,21 +155,26 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        rows = []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in out.strip().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[1]), float(f[2]), [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        inside = [r for r in rows if window is None or window[0] <= r[0] <= window[1]]
+        where = "timed region"
+        if not inside:
+            inside, where = rows, "warm-up + timed region (no sample fell inside the timed region itself)"
+        sm, mx = [r[1] for r in inside], [r[2] for r in inside]
+        reasons = sorted({n for r in inside for n in r[3]})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "window": where}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -236,6 +255,205 @@ def run_reference(args):
     _ = t_start
 
 
+
+# ------------------------------------------------------------------------------------------------
+# sub-records: the other BASELINE configs, measured by the same process after the headline workload
+# ------------------------------------------------------------------------------------------------
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(csv_name, kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, one launch) of `kernel` from a committed ncu capture."""
+    cap = os.path.join(ROOT, "profiles", csv_name)
+    if not os.path.exists(cap):
+        return None, None
+    for row in open(cap):
+        f = row.strip().split(",")
+        if kernel in f[0]:
+            try:
+                return (float(f[2]) + float(f[3])) * 1e6, "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, one launch)" % csv_name
+            except (ValueError, IndexError):
+                continue
+    return None, None
+
+
+def solver_roofline(ctr, solve_ms, kernel, traffic_csv=None):
+    """SURVEY.md section 8d, solve-stage terms: 964 B per manifold + 376 B per contact per launch."""
+    peak, peak_src = hbm_peak()
+    M, Q = ctr["manifolds"], ctr["contacts"]
+    nbytes = 964.0 * M + 376.0 * Q
+    achieved = nbytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
+    traffic, src = ncu_traffic(traffic_csv, kernel) if traffic_csv else (None, None)
+    return {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "traffic_source": src, "peak_source": peak_src, "bytes_per_launch": nbytes, "ms_per_launch": solve_ms}
+
+
+def timed_world_steps(L, world, dt, steps, flush):
+    """`steps` frStepWorld calls, each in its own CUDA-event bracket on the world's stream (L2 flushed outside the
+    bracket when asked), with the per-stage events on: (per-step ms, stage means, counters, launches)."""
+    import ferox_b200 as fb
+    ms = np.zeros(steps, np.float32)
+    L.frxSetProfiling(world, 1)
+    l0 = L.frxGetLaunchCount()
+    L.frxTimedSteps(world, dt, steps, 1 if flush else 0, ms)
+    launches = L.frxGetLaunchCount() - l0
+    stage = (C.c_double * 5)()
+    k = L.frxGetStageTimes(world, stage)
+    L.frxSetProfiling(world, 0)
+    ctr = fb.step_counters(L, world)
+    names = ["broadphase", "narrowphase", "cache", "solve", "integrate"]
+    return ms, {n: stage[i] / max(1, k) for i, n in enumerate(names)}, ctr, int(launches)
+
+
+def sub_config1(L, dt):
+    """configs[0]: 128 x 8 boxes + ground, cell 1.5; 1 priming step (bodies enter) + 600 timed steps from the drop."""
+    import ferox_b200 as fb
+    from ferox_b200 import scenes
+    spec = scenes.box_stack(128, 8)
+    sc = scenes.Scene(L, spec, prime=False)
+    L.frStepWorld(sc.world, dt)
+    ms, stage, ctr, launches = timed_world_steps(L, sc.world, dt, 600, True)
+    st = fb.body_states(L, sc.world)
+    fb.check_error(L)
+    out = {"workload": "config1: 1,024 boxes (128 x 8) on static ground, cell 1.5, dt 1/60, 1 priming + 600 timed steps, L2 flushed between steps",
+           "bodies": spec.n, "steps": 600, "ms_per_step": float(ms.mean()), "value": spec.n * 600 / (float(ms.sum()) * 1e-3), "unit": UNIT,
+           "stage_ms_per_step": stage, "counters": ctr, "gpu_launches": launches,
+           "kinetic_energy_proxy": float((st["vel"].astype(np.float64) ** 2).sum()), "max_y": float(st["pos"][:, 1].max()),
+           "roofline": solver_roofline(ctr, stage["solve"], "k_solve_local (block-local solver: the world fits one CTA)")}
+    sc.release()
+    return out
+
+
+def sub_config3(L, dt, bodies=1048576):
+    """configs[2] as SURVEY.md section 8d specifies it: the column COLLAPSE itself is the timed region."""
+    import ferox_b200 as fb
+    from ferox_b200 import scenes
+    spec = scenes.column_collapse(bodies)
+    sc = build_bulk_world(L, spec)
+    L.frStepWorld(sc.world, dt)                      # priming step: queued bodies enter the world
+    n = L.frGetBodyCountInWorld(sc.world)
+    out = {"workload": "config3: %d uniform circles (r 0.5), column 512 wide x %d high (pitch 1.05, jitter 0.02, seed 1), left wall, right "
+                       "wall removed at t = 0, static floor 16,384 units wide, cell 2.0, dt 1/60; the 600 steps of the collapse are the "
+                       "timed region (per-step working set > 2 GB, far larger than the 126 MB L2)" % (bodies, (bodies + 511) // 512),
+           "bodies": n, "steps": 600}
+    ms_all, marks = [], {}
+    for chunk in range(6):
+        ms, stage, ctr, launches = timed_world_steps(L, sc.world, dt, 100, False)
+        ms_all.append(ms)
+        marks["step_%d" % (100 * (chunk + 1))] = {"ms_per_step": float(ms.mean()), "counters": {k: ctr[k] for k in ("cellEntries", "candidates", "manifolds", "contacts", "colors", "overflow")},
+                                                  "stage_ms_per_step": stage}
+        if L.frxGetLastError():
+            break
+    ms_all = np.concatenate(ms_all)
+    st = fb.body_states(L, sc.world)
+    speed = np.linalg.norm(st["vel"], axis=1)
+    out.update({"steps": int(len(ms_all)), "ms_per_step": float(ms_all.mean()), "ms_per_step_max": float(ms_all.max()),
+                "hz": 1e3 / float(ms_all.mean()), "hz_worst_step": 1e3 / float(ms_all.max()),
+                "value": n * len(ms_all) / (float(ms_all.sum()) * 1e-3), "unit": UNIT,
+                "overflow": int(ctr["overflow"]), "error": L.frxGetLastErrorString().decode() if L.frxGetLastError() else None,
+                "finite": bool(np.isfinite(st["pos"]).all() and np.isfinite(st["vel"]).all()),
+                "mean_speed": float(speed.mean()), "max_speed": float(speed.max()),
+                "extent_x": [float(st["pos"][:, 0].min()), float(st["pos"][:, 0].max())],
+                "extent_y": [float(st["pos"][:, 1].min()), float(st["pos"][:, 1].max())],
+                "history": marks, "gpu_launches_last_100": launches,
+                "roofline": solver_roofline(ctr, stage["solve"], "k_solve_colored", "r02_config3_top_kernels_ncu.csv"),
+                "roofline_narrowphase": narrow_roofline(ctr, stage["narrowphase"]),
+                "roofline_broadphase": broad_roofline(n, ctr, stage["broadphase"])})
+    L.frxClearLastError()
+    sc.release()
+    return out
+
+
+def narrow_roofline(ctr, ms):
+    peak, src = hbm_peak()
+    nbytes = ctr["candidates"] * (64.0 + 8.0) + 96.0 * ctr["manifolds"]      # SURVEY 8d: C (64 + G) + 96 M, circles: G = 8
+    a = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": "k_narrowphase_tiled", "achieved": a, "peak": peak, "unit": "GB/s", "frac": a / peak,
+            "bytes_per_launch": nbytes, "ms_per_launch": ms, "peak_source": src}
+
+
+def broad_roofline(n, ctr, ms):
+    peak, src = hbm_peak()
+    K, Cn = ctr["cellEntries"], ctr["candidates"]
+    nbytes = n * (52.0 + 36.0 + 4.0) + 8.0 * K + 68.0 * K + 28.0 * K + 8.0 * Cn     # SURVEY 8d break-down, S = 4
+    a = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    return {"bound": "hbm", "kernel": "broadphase stage (prepass, entry emission, radix sort passes, pair emission)", "achieved": a,
+            "peak": peak, "unit": "GB/s", "frac": a / peak, "bytes_per_launch": nbytes, "ms_per_launch": ms, "peak_source": src}
+
+
+def build_config5_strip(L, per_strip, rank, world_size, local_rank, dist, margin, ghost_cap):
+    """This rank's strip of ONE pile of world_size x per_strip bodies; neighbours linked through the library's own NCCL
+    communicator (the 128-byte id travels over torch.distributed)."""
+    from ferox_b200 import scenes
+    spec, lo, hi = scenes.strip_pile(per_strip, rank, world_size, storeys=8)
+    sc = scenes.StripScene.local(L, spec, rank, world_size, lo, hi, margin=margin, ghost_cap=ghost_cap, device=local_rank)
+    sc.world = sc.worlds[0]
+    if world_size > 1:
+        import torch
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (C.c_ubyte * 128)()
+            assert L.frxStripGetNcclUniqueId(buf) == 0, L.frxGetLastErrorString()
+            uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
+        uid = uid.to(torch.device("cuda", local_rank))
+        dist.broadcast(uid, 0)
+        assert L.frxStripInitNccl(sc.world, rank, world_size, uid.cpu().numpy().tobytes()) == 0, L.frxGetLastErrorString()
+    sc.step(1)
+    return sc, spec
+
+
+def measure_config4(L, dt, n_worlds, rank, world_size, steps, barrier, reduce_max):
+    """`n_worlds` independent 256-body worlds sharded round-robin over `world_size` ranks; returns (total bodies of this
+    rank, elapsed ms of the timed steps MAX-reduced, stage means, counters)."""
+    sc = build_config4_batch(L, n_worlds, rank, world_size)
+    L.frStepWorld(sc.world, dt)
+    n = L.frGetBodyCountInWorld(sc.world)
+    L.frxStepWorldN(sc.world, dt, 300)
+    L.frxSynchronizeWorld(sc.world)
+    barrier()
+    ms, stage, ctr, launches = timed_world_steps(L, sc.world, dt, steps, True)
+    barrier()
+    elapsed = reduce_max(float(ms.sum()))
+    sc.release()
+    return n, elapsed, stage, ctr, launches, sc.n_worlds
+
+
+def _ref_small_world_worker(args):
+    k, steps, q = args
+    from ferox_b200 import capi, scenes
+    lib = capi.load_abi(os.path.join(ROOT, "oracle", "_ref", "libferox_ref_2048.so"))
+    sc = scenes.Scene(lib, scenes.small_world(k))
+    sc.step(300)
+    t0 = time.perf_counter()
+    sc.step(steps)
+    q.put((sc.spec.n, steps, time.perf_counter() - t0))
+
+
+def config4_cpu_baseline(steps=200):
+    """the UNMODIFIED reference, one 256-body world per process on every host core."""
+    lib = os.path.join(ROOT, "oracle", "_ref", "libferox_ref_2048.so")
+    if not os.path.exists(lib):
+        return None
+    cores = max(1, min(os.cpu_count() or 1, 64))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_ref_small_world_worker, args=((k, steps, q),)) for k in range(cores)]
+    for p in ps:
+        p.start()
+    done = [q.get() for _ in ps]
+    for p in ps:
+        p.join()
+    wall = max(d[2] for d in done)
+    return {"value": sum(d[0] for d in done) * steps / wall, "unit": UNIT, "cores": cores, "kind": "reference",
+            "world_steps_per_s": cores * steps / wall,
+            "sample": "%d processes, each the unmodified reference (FR_WORLD_MAX_OBJECT_COUNT 2048) stepping one config-4 world "
+                      "(256 bodies, settled 300 steps) %d times; aggregate over the processes, slowest process's wall clock" % (cores, steps)}
+
+
 # ------------------------------------------------------------------------------------------------
 # the product arm
 # ------------------------------------------------------------------------------------------------
@@ -268,20 +486,7 @@ def run_b200(args):
         L.frStepWorld(sc.world, dt)
         n = L.frGetBodyCountInWorld(sc.world)
     elif strips:
-        spec, lo, hi = scenes.strip_pile(args.bodies, rank, world_size, storeys=8)
-        sc = scenes.StripScene.local(L, spec, rank, world_size, lo, hi, margin=args.margin, ghost_cap=args.ghost_cap, device=local_rank)
-        sc.world = sc.worlds[0]
-        if world_size > 1:
-            import torch
-            uid = torch.zeros(128, dtype=torch.uint8)
-            if rank == 0:
-                buf = (C.c_ubyte * 128)()
-                assert L.frxStripGetNcclUniqueId(buf) == 0, L.frxGetLastErrorString()
-                uid = torch.frombuffer(bytearray(buf), dtype=torch.uint8).clone()
-            uid = uid.to(torch.device("cuda", local_rank))
-            dist.broadcast(uid, 0)
-            assert L.frxStripInitNccl(sc.world, rank, world_size, uid.cpu().numpy().tobytes()) == 0, L.frxGetLastErrorString()
-        sc.step(1)
+        sc, spec = build_config5_strip(L, args.bodies, rank, world_size, local_rank, dist, args.margin, args.ghost_cap)
         n = L.frGetBodyCountInWorld(sc.world)
         assert n == spec.n, (n, spec.n)
     else:
@@ -308,16 +513,17 @@ def run_b200(args):
     fb.check_error(L)
 
     warm = max(3, args.warmup)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                  # nvidia-smi needs a few hundred ms before its first sample
     step_n(warm)
     L.frxSynchronizeWorld(sc.world)
 
     # ---- timed region A: device-resident state, per-step CUDA events, cold L2 ----
-    sampler = ClockSampler(local_rank)
     ms = np.zeros(args.steps, np.float32)
     L.frxSetProfiling(sc.world, 1)
     launches0 = L.frxGetLaunchCount()
     barrier()
-    sampler.start()
+    t_region0 = time.time()
     ncu_range = os.environ.get("FEROX_NCU_RANGE") == "1"     # `ncu --profile-from-start off` captures only this span
     if ncu_range:
         L.frxProfilerRange(1)
@@ -332,7 +538,8 @@ def run_b200(args):
         L.frxTimedSteps(sc.world, dt, args.steps, 1, ms)
     if ncu_range:
         L.frxProfilerRange(0)
-    clocks = sampler.stop()
+    L.frxSynchronizeWorld(sc.world)
+    clocks = sampler.stop((t_region0 - 0.02, time.time() + 0.02))
     barrier()
     launches = L.frxGetLaunchCount() - launches0
     stage_ms = (C.c_double * 5)()
@@ -397,6 +604,23 @@ def run_b200(args):
     e2e_s, checksum = e2e_loop(False)
     e2e_copy_s, _ = e2e_loop(True)
     fb.check_error(L)
+
+    # ---- the loop an EXISTING ferox program runs, through ferox.h alone and compiled C (tests/c/e2e_loop.c): one
+    # frApplyForceToBody per body, frStepWorld, one frGetBodyPosition per body ----
+    ferox_h = None
+    loop_path = os.path.join(ROOT, "ferox_b200", "_build", "libfx_e2e_loop.so")
+    if not strips and args.workload == "config2" and rank == 0 and os.path.exists(loop_path):
+        loop = C.CDLL(loop_path)
+        loop.fx_e2e_ferox_h_loop.restype = C.c_double
+        loop.fx_e2e_ferox_h_loop.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_double)]
+        chk = C.c_double()
+        hsteps = max(5, min(50, args.steps))
+        loop.fx_e2e_ferox_h_loop(sc.world, 2, dt, 0.01, 0.0, C.byref(chk))
+        secs = loop.fx_e2e_ferox_h_loop(sc.world, hsteps, dt, 0.01, 0.0, C.byref(chk))
+        ferox_h = {"value": n * hsteps / secs, "unit": UNIT, "ms_per_step": 1e3 * secs / hsteps, "steps": hsteps, "checksum": chk.value,
+                   "api": "ferox.h only, compiled C (tests/c/e2e_loop.c): per step n x frApplyForceToBody(b, frGetBodyPosition(b), f), "
+                          "frStepWorld, n x frGetBodyPosition; 16 B/body up, 16 B/body (positions) + 16 B/body (velocities on first getter) down"}
+        fb.check_error(L)
 
     # ---- the same steps with a (no-op, compiled C) collision handler installed: every live manifold goes to the
     # host before and after the solve and comes back (SURVEY.md section 8d asks for this second number) ----
@@ -493,7 +717,8 @@ def run_b200(args):
                     "checksum": checksum,
                     "api": "frxMapBodyForces + frStepWorld (frxStripStep on a strip) + frxViewBodyStates (forces written into, states read from the library's pinned host mirror)",
                     "value_copy_out": total_bodies * e2e_steps / e2e_copy_s,
-                    "api_copy_out": "frxApplyForces + step + frxGetBodyStates (caller-owned pageable arrays in, 6 caller-owned arrays out)"},
+                    "api_copy_out": "frxApplyForces + step + frxGetBodyStates (caller-owned pageable arrays in, 6 caller-owned arrays out)",
+                    "ferox_h_loop": ferox_h},
             "handler_bridge": None if handler_ms is None else {
                 "ms_per_step": handler_ms, "value": n / (handler_ms * 1e-3), "unit": UNIT,
                 "note": "rank 0, wall clock, no-op C pre+post handlers installed: %d callbacks over the sample" % handler_calls},
@@ -502,12 +727,114 @@ def run_b200(args):
         }
         if not args.no_cpu_baseline and args.workload == "config2":
             line["cpu_baseline"] = cpu_baseline(sc, n)
+    barrier()
+    sc.release()
+
+    # ---- sub-records: the other BASELINE configs on the same build, same process (every rank takes part at N > 1) ----
+    if not args.skip_sub and args.workload == "config2":
+        sub = run_sub_records(L, args, rank, world_size, local_rank, dist, barrier)
+        if rank == 0:
+            line.update(sub)
+    if rank == 0:
         print(json.dumps(line))
         sys.stdout.flush()
     barrier()
-    sc.release()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
+    import ferox_b200 as fb
+    from ferox_b200 import scenes
+    dt = scenes.DT
+    out = {}
+
+    def reduce_max(x):
+        if dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64, device=torch.device("cuda", local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def reduce_sum(x):
+        if dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], dtype=torch.float64, device=torch.device("cuda", local_rank))
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    def guarded(name, fn):
+        # a sub-record must never take the headline down with it: report the failure in its place
+        try:
+            return fn()
+        except Exception as e:                                   # noqa: BLE001
+            L.frxClearLastError()
+            return {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+
+    steps = args.sub_steps
+    if world_size == 1:
+        out["config1"] = guarded("config1", lambda: sub_config1(L, dt))
+        out["config3"] = guarded("config3", lambda: sub_config3(L, dt))
+
+        def c4():
+            n, elapsed, stage, ctr, launches, nw = measure_config4(L, dt, args.worlds, 0, 1, steps, barrier, reduce_max)
+            rec = {"workload": "config4: %d independent worlds x 256 bodies (252 dynamic mixed + floor + 2 walls + kinematic paddle), ONE batch "
+                               "(one launch set per step for all worlds), settled 300 steps, L2 flushed between timed steps" % nw,
+                   "bodies": n, "worlds": nw, "steps": steps, "ms_per_step": elapsed / steps, "value": n * steps / (elapsed * 1e-3), "unit": UNIT,
+                   "world_steps_per_s": nw * steps / (elapsed * 1e-3), "stage_ms_per_step": stage, "counters": ctr, "gpu_launches": launches,
+                   "roofline": solver_roofline(ctr, stage["solve"], "k_solve_local (one CTA per sub-world, velocities in shared memory)")}
+            if not args.no_cpu_baseline:
+                rec["cpu_baseline"] = config4_cpu_baseline()
+            return rec
+        out["config4"] = guarded("config4", c4)
+        return out
+
+    # ---- N > 1: the two splits north_star names ----
+    def c4_multi():
+        n, elapsed, stage, ctr, launches, nw = measure_config4(L, dt, args.worlds, rank, world_size, steps, barrier, reduce_max)
+        total = reduce_sum(n)
+        strong = {"worlds_total": args.worlds, "worlds_per_gpu": nw, "bodies_total": int(total), "ms_per_step": elapsed / steps,
+                  "value": total * steps / (elapsed * 1e-3), "unit": UNIT, "stage_ms_per_step_rank0": stage}
+        n, elapsed, stage, ctr, launches, nw = measure_config4(L, dt, args.worlds, 0, 1, steps, barrier, reduce_max)
+        total = reduce_sum(n)
+        weak = {"worlds_total": args.worlds * world_size, "worlds_per_gpu": nw, "bodies_total": int(total), "ms_per_step": elapsed / steps,
+                "value": total * steps / (elapsed * 1e-3), "unit": UNIT, "stage_ms_per_step_rank0": stage}
+        return {"workload": "config4: independent 256-body worlds, one batch per GPU, no data-path communication; strong = %d worlds "
+                            "sharded round-robin over %d GPUs, weak = %d worlds on every GPU; MAX over ranks of the device time of "
+                            "%d steps (L2 flushed between steps)" % (args.worlds, world_size, args.worlds, steps),
+                "n_gpus": world_size, "steps": steps, "strong": strong, "weak": weak}
+    out["config4"] = guarded("config4", c4_multi)
+
+    def c5_multi():
+        sc, spec = build_config5_strip(L, 1048576, rank, world_size, local_rank, dist, args.margin, args.ghost_cap)
+        n = L.frGetBodyCountInWorld(sc.world)
+        sc.step(600)
+        L.frxSynchronizeWorld(sc.world)
+        sc.step(3)
+        L.frxSynchronizeWorld(sc.world)
+        barrier()
+        L.frxRecordEvent(sc.world, 0)
+        sc.step(steps)
+        L.frxRecordEvent(sc.world, 1)
+        elapsed = reduce_max(float(L.frxEventElapsedMs(sc.world, 0, 1)))
+        barrier()
+        ctr = fb.step_counters(L, sc.world)
+        total = reduce_sum(n)
+        over = reduce_max(float(ctr["overflow"]))
+        err = L.frxGetLastErrorString().decode() if L.frxGetLastError() else None
+        L.frxClearLastError()
+        sc.release()
+        return {"workload": "config5: ONE pile of %d x 1,048,576 mixed bodies on 8 storeys cut into %d vertical strips, one per GPU; ghost "
+                            "rows (96 B) once per step and 16-byte velocity changes after each of the 11 solver stages exchanged between "
+                            "neighbours with the library's own NCCL communicator (ncclSend/ncclRecv); settled 600 steps; one event bracket "
+                            "around %d steps, MAX over ranks (per-step working set > 2 GB per GPU)" % (world_size, world_size, steps),
+                "n_gpus": world_size, "nccl_ranks": world_size, "bodies_total": int(total), "steps": steps, "ms_per_step": elapsed / steps,
+                "hz": 1e3 * steps / elapsed, "value": total * steps / (elapsed * 1e-3), "unit": UNIT, "counters_rank0": ctr,
+                "overflow_max_over_ranks": int(over), "error_rank0": err}
+    out["config5"] = guarded("config5", c5_multi)
+    return out
 
 
 def cpu_baseline(sc, n):
