@@ -21,6 +21,7 @@ Sub-records in the same line (driver-witnessed, each a bounded run of the same b
   config1   BASELINE configs[0]: 1,024 boxes on static ground, 1 priming + 600 timed steps
   config3   BASELINE configs[2]: 1,048,576 uniform circles, 512 x 2,048 column, right wall removed at t = 0, on a
             16,384-unit floor -- the 600 steps of the collapse, timed; Hz, overflow, per-kernel roofline
+  config3_shallow  the same 1 M circles as a bed the reference's solver can hold up (the column recipe overruns it)
   config4   BASELINE configs[3]: 4,096 independent worlds x 256 bodies.  N = 1: one batch on the GPU + the CPU
             baseline (unmodified reference, one world per process on every host core).  N > 1: the worlds
             sharded round-robin over the ranks (strong scaling) AND 4,096 worlds on every rank (weak scaling)
@@ -360,10 +361,42 @@ def sub_config3(L, dt, bodies=1048576):
                 "extent_x": [float(st["pos"][:, 0].min()), float(st["pos"][:, 0].max())],
                 "extent_y": [float(st["pos"][:, 1].min()), float(st["pos"][:, 1].max())],
                 "history": marks, "gpu_launches_last_100": launches,
-                "roofline": solver_roofline(ctr, stage["solve"], "k_solve_colored", "r02_config3_top_kernels_ncu.csv"),
+                "note": "the reference's own arithmetic does not hold this column up: 10 sweeps per step cannot carry 2,000 rows, the column "
+                        "telescopes into the floor in free fall and bursts later (oracle beside the GPU, bit for bit on a 16-column slice: "
+                        "tests/test_gpu_large.py::test_config3_column_recipe_overruns_the_reference_solver_too); steady-state 1 M-body "
+                        "figures: config3_shallow",
+                "roofline": solver_roofline(ctr, stage["solve"], "k_solve_colored"),
                 "roofline_narrowphase": narrow_roofline(ctr, stage["narrowphase"]),
                 "roofline_broadphase": broad_roofline(n, ctr, stage["broadphase"])})
     L.frxClearLastError()
+    sc.release()
+    return out
+
+
+def sub_config3_shallow(L, dt, bodies=1048576, steps=200):
+    """The same 1,048,576 uniform circles as a bed the reference's solver CAN hold up (8 storeys x 16 lattice rows),
+    settled 600 steps: the steady-state figure for a 1 M-body world, beside the column recipe that overruns the
+    solver (tests/test_gpu_large.py::test_config3_column_recipe_overruns_the_reference_solver_too)."""
+    import ferox_b200 as fb
+    from ferox_b200 import scenes
+    spec, _, _ = scenes.strip_pile(bodies, 0, 1, seed=1, storeys=8, max_rows=16, circle_fraction=1.0)
+    sc = build_bulk_world(L, spec)
+    L.frStepWorld(sc.world, dt)
+    n = L.frGetBodyCountInWorld(sc.world)
+    L.frxStepWorldN(sc.world, dt, 600)
+    L.frxSynchronizeWorld(sc.world)
+    ms, stage, ctr, launches = timed_world_steps(L, sc.world, dt, steps, False)
+    st = fb.body_states(L, sc.world)
+    fb.check_error(L)
+    speed = np.linalg.norm(st["vel"], axis=1)
+    out = {"workload": "config3_shallow: %d uniform circles (r 0.5) on 8 storeys x 16 lattice rows, walled, cell 2.0, dt 1/60, settled 600 "
+                       "steps (per-step working set > 2 GB, far larger than the 126 MB L2)" % bodies,
+           "bodies": n, "steps": steps, "ms_per_step": float(ms.mean()), "hz": 1e3 / float(ms.mean()), "value": n * steps / (float(ms.sum()) * 1e-3),
+           "unit": UNIT, "stage_ms_per_step": stage, "counters": ctr, "gpu_launches": launches, "overflow": int(ctr["overflow"]),
+           "mean_speed": float(speed.mean()), "max_speed": float(speed.max()),
+           "roofline": solver_roofline(ctr, stage["solve"], "k_solve_colored", "r02_config3_top_kernels_ncu.csv"),
+           "roofline_narrowphase": narrow_roofline(ctr, stage["narrowphase"]),
+           "roofline_broadphase": broad_roofline(n, ctr, stage["broadphase"])}
     sc.release()
     return out
 
@@ -777,6 +810,7 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
     if world_size == 1:
         out["config1"] = guarded("config1", lambda: sub_config1(L, dt))
         out["config3"] = guarded("config3", lambda: sub_config3(L, dt))
+        out["config3_shallow"] = guarded("config3_shallow", lambda: sub_config3_shallow(L, dt))
 
         def c4():
             n, elapsed, stage, ctr, launches, nw = measure_config4(L, dt, args.worlds, 0, 1, steps, barrier, reduce_max)

@@ -187,8 +187,8 @@ __device__ __forceinline__ bool plan_keys(const DevWorld &w, bool publish, unsig
     unsigned int passes = (bits + 7) / 8;
     if ((int) passes > (w.sort_launch > 0 ? w.sort_launch : 8)) {
         // the host launched fewer digit passes than these keys need (it sizes them from the previous step's key width
-        // plus one bit, and launches all eight after any setter moved a body): the world's extent more than doubled
-        // within one step of free motion.  Refuse loudly, emit nothing; the next step re-measures.
+        // plus one digit, and launches all eight after any setter moved a body): the world's extent grew more than
+        // 256-fold within one step of free motion.  Refuse loudly, emit nothing; the next step re-measures.
         ok = false;
         passes = 0;
     }

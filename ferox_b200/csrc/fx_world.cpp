@@ -689,10 +689,11 @@ static void fill_dev_params(frWorld *w, float dt) {
     }
     d.solver_mode = w->solver_mode;
     {
-        // digit passes of the broadphase sort: all four until a step has told us the key width, then what that width
-        // plus one bit needs (k_plan refuses a step whose keys need more than was launched)
+        // digit passes of the broadphase sort: all eight until a step has told us the key width, then what that width
+        // plus one whole digit needs: the world's cell extent may grow 256-fold from one step to the next (free motion
+        // grows it by a few cells) before plan_keys has to refuse a step for want of launched passes
         const unsigned int bits = w->last.key_bits;
-        d.sort_launch = (bits == 0u || w->needs_sizing || w->extent_unknown) ? FX_SORT_MAX_PASSES : (int) ((bits + 1u + 7u) / 8u);
+        d.sort_launch = (bits == 0u || w->needs_sizing || w->extent_unknown) ? FX_SORT_MAX_PASSES : (int) ((bits + 8u + 7u) / 8u);
         if (d.sort_launch > FX_SORT_MAX_PASSES) d.sort_launch = FX_SORT_MAX_PASSES;
     }
     { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }

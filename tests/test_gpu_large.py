@@ -131,7 +131,7 @@ def test_forced_large_variants_colored_mode_same_bits_as_small_variants(gpu, mon
         sc.release()
     assert_states_equal(out[0][0], out[1][0], "forced-large vs default")
     assert_caches_equal(out[0][1], out[1][1], "manifolds", timestamps=True)
-    assert out[0][2]["colors"] == out[1][2]["colors"] and out[0][2]["manifolds"] > 9000
+    assert out[0][2]["colors"] == out[1][2]["colors"] and out[0][2]["manifolds"] > 6000
 
 
 # ------------------------------------------------------------------------------------------------
@@ -160,7 +160,7 @@ def test_config2_full_size_reference_order_vs_oracle(gpu, monkeypatch, large):
     oc = ow.counters()
     assert c["overflow"] == 0 and c["cellEntries"] == oc["K"] and c["candidates"] == oc["C"] and c["manifolds"] == oc["M"] \
         and c["contacts"] == oc["Q"], (c, oc)
-    assert c["manifolds"] > 100000                      # a deep pile, not a falling lattice
+    assert c["manifolds"] > 80000                       # a deep pile, not a falling lattice
     assert_states_equal(fb.body_states(L, sc.world), ow.state(), "config 2, 20 reference-order steps")
     sc.release(); ow.close()
 
@@ -191,4 +191,25 @@ def test_262k_bodies_one_step_pairs_and_contacts_vs_oracle(gpu):
     key = lambda a, b: a.astype(np.int64) * (1 << 32) + b
     m = m[np.isin(key(m["a"], m["b"]), key(hits[:, 0], hits[:, 1]))]
     assert_geometry_equal(m, ow.cache(), "262k bodies")
+    sc.release(); ow.close()
+
+
+def test_config3_column_recipe_overruns_the_reference_solver_too(gpu):
+    """SURVEY.md section 8d's config 3 (column 2,048 rows high, lattice pitch 1.05) on a 16-column slice, next to the
+    oracle: the reference's own arithmetic does not hold such a column up -- 10 Gauss-Seidel sweeps per step cannot
+    carry the weight of 2,000 rows, the column telescopes into the floor in free fall (mean speed = g t) and
+    later bursts -- and the GPU step reproduces that trajectory BIT FOR BIT in reference order.  bench.py therefore
+    reports the full-size recipe as it is (`config3`) and a shallow 1 M-circle bed beside it (`config3_shallow`)."""
+    L = gpu
+    spec = scenes.column_collapse(16 * 2048, cols=16)
+    sc = make_world(L, spec, fb.SOLVER_SERIAL)
+    ow = orc.OracleWorld.from_scene(sc)
+    L.frxStepWorldN(sc.world, DT, 300)
+    ow.step(300)
+    fb.check_error(L)
+    got, want = fb.body_states(L, sc.world), ow.state()
+    assert_states_equal(got, want, "column slice, 300 reference-order steps")
+    speed = np.linalg.norm(want["vel"][2:], axis=1)
+    assert speed.mean() > 0.8 * 9.8 * 300 * DT             # still falling freely through itself after 5 s
+    assert fb.step_counters(L, sc.world)["manifolds"] < spec.n // 2
     sc.release(); ow.close()
