@@ -700,17 +700,17 @@ def run_b200(args):
         solve_ms = solve_ms_total / max(1, prof_steps)
         achieved = solve_bytes / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else 0.0
         step_bytes = (n * (160 + 2 * 24) + 104 * ctr["cellEntries"] + ctr["candidates"] * (64 + 92) + 1060 * M + 376 * Q)
-        roof_kernel = "k_solve_colored"
+        kind = L.frxGetWorldSolverKernel(sc.world) if hasattr(L, "frxGetWorldSolverKernel") else 0
+        roof_kernel = ("k_solve_colored" if kind == 0 else "k_solve_local" if kind < 0 else
+                       "solve stage = k_solve_colored (colouring, ordering, records; full grid) + k_sweep_cluster (warm start + 10 sweeps "
+                       "in one %d-CTA thread-block cluster, velocities in distributed shared memory)" % kind)
         traffic, traffic_src = None, None
         if args.workload == "config2" and args.bodies == 65536:
             # DRAM bytes of that kernel from the committed `ncu --set full` capture of this same command
-            cap = os.path.join(ROOT, "profiles", "r01_end_top_kernels_ncu.csv")
-            if os.path.exists(cap):
-                for row in open(cap):
-                    f = row.strip().split(",")
-                    if "k_solve_colored" in f[0]:
-                        traffic = (float(f[2]) + float(f[3])) * 1e6
-                        traffic_src = "profiles/r01_end_top_kernels_ncu.csv (dram__bytes_read.sum + dram__bytes_write.sum, one launch)"
+            if kind > 0:
+                traffic, traffic_src = ncu_traffic("r02_config2_top_kernels_ncu.csv", "k_sweep_cluster")
+            else:
+                traffic, traffic_src = ncu_traffic("r01_end_top_kernels_ncu.csv", "k_solve_colored")
         if strips:
             # the strip step runs the solver as 12 separately launched stages with an exchange after each; there
             # are no per-stage events, so the roofline line is the WHOLE step of this rank's strip

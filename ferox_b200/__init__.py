@@ -77,6 +77,7 @@ EXT_PROTOTYPES = {
     "frxEventElapsedMs": (F, [P, I, I]),
     "frxGetLaunchCount": (C.c_longlong, []),
     "frxGetGraphReplays": (C.c_longlong, [P]),
+    "frxGetWorldSolverKernel": (I, [P]),
     "frxProfilerRange": (None, [I]),
     "frxTimedSteps": (I, [P, F, I, I, f32p]),
 }

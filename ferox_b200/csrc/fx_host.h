@@ -93,6 +93,8 @@ struct frWorld_ {
     unsigned int d_gorder_cap = 0;
     int local_max_bodies = 0;        // 0: not eligible (some sub-world's bodies are not one short index range)
     int use_local = 1;
+    int cluster_size = 0;            // > 0: the solve runs in one thread-block cluster of this many CTAs (fx_solve.cu k_sweep_cluster)
+    int cluster_bodies = -1;         // body count cluster_size was decided for
     int force_large = 0;             // FEROX_FORCE_LARGE=1: the large-world kernel variants at any size (parity tests)
 
     HostMirror h;

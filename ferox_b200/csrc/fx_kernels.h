@@ -68,6 +68,9 @@ void fx_launch_cache_update(const DevWorld &w, const FxLaunchCtx &cx);
 void fx_launch_solve_local(const DevWorld &w, const FxLaunchCtx &cx, int iterations, int max_bodies);
 int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint);
 void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint, int phases = 7);
+#define FX_CLUSTER_MAX_SMEM (220 * 1024)
+int fx_cluster_size_for(int bodies);       // 16 / 8: the world's velocities fit one cluster's distributed shared memory; 0: they do not
+void fx_launch_solve_cluster(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint, int cluster_size);
 void fx_launch_serial_order(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o);
 void fx_launch_solve_serial_with(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, int iterations);
 void fx_launch_integrate_position(const DevWorld &w, const FxLaunchCtx &cx);

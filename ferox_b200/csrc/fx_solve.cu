@@ -59,31 +59,61 @@ __device__ __forceinline__ bool body_is_written(const DevWorld &w, int i) {
     return w.vel[i].w > 0.0f || w.mprop[i].y > 0.0f;
 }
 
-// build the solver record of manifold m at slot s and apply its warm start (src/rigid_body.c:333-411)
-__device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const ManifoldSet &man, unsigned int m,
-                                                       unsigned int s, float4 *vel, int lo, float inv_dt) {
+// Where the sweeps find a body's velocity {vx, vy, omega, invMass}: the world array (or a block's shared-memory copy
+// of an index range of it), or -- k_sweep_cluster -- the distributed shared memory of a thread-block cluster.  The
+// arithmetic below is written once against this accessor, so every solver kernel produces the same bits.
+struct VelArray {
+    float4 *p;
+    int lo;
+    __device__ __forceinline__ float4 load(int i) const { return p[i - lo]; }
+    __device__ __forceinline__ void store(int i, float4 v) const { p[i - lo] = v; }
+};
+
+// solver record word `count_src`: [1:0] contacts to solve (0: both bodies immovable), [2] / [3] body A / B is STATIC and is
+// brought to rest by the warm start of such a manifold (src/rigid_body.c:339-347), [31:4] source manifold index
+#define CS_COUNT(cs) ((cs) & 3)
+#define CS_ZERO_A 4
+#define CS_ZERO_B 8
+#define CS_SRC(cs) ((unsigned int) (cs) >> 4)
+
+// what the warm start of one manifold needs (all of it is in its solver record)
+struct WarmRec {
+    int2 b;
+    int cs;
+    float4 nt, mat;      // {n, t}, {friction, restitution, invInertiaA, invInertiaB}
+    float4 r[2];         // lever arms of the (up to) two contacts
+    float2 lam[2];       // cached impulses
+};
+
+// build the solver record of manifold m at slot s: everything that depends on positions only (src/rigid_body.c:350-385)
+__device__ __forceinline__ WarmRec build_record(const DevWorld &w, const ManifoldSet &man, unsigned int m, unsigned int s, float inv_ma,
+                                                float inv_mb, float inv_dt) {
+    WarmRec q;
     const int2 b = man.body[m];
     const float4 hdr = man.hdr[m];
     const int count = man.meta[m].x;
     const V2 n = v2(hdr.x, hdr.y);
     const V2 t = vperp_right(n);
-    float4 va4 = vel[b.x - lo], vb4 = vel[b.y - lo];
-    const float inv_ma = va4.w, inv_mb = vb4.w;
-    const float inv_ia = w.mprop[b.x].y, inv_ib = w.mprop[b.y].y;
+    const float4 mpa = w.mprop[b.x], mpb = w.mprop[b.y];
+    const float inv_ia = mpa.y, inv_ib = mpb.y;
     const float4 pa4 = w.posrot[b.x], pb4 = w.posrot[b.y];
-    w.sol.body[s] = b;
-    w.sol.nt[s] = make_float4(n.x, n.y, t.x, t.y);
-    w.sol.mat[s] = make_float4(hdr.z, hdr.w, inv_ia, inv_ib);
     const bool active = (inv_ma + inv_mb > 0.0f);           // src/rigid_body.c:338
-    w.sol.count_src[s] = (active ? count : 0) | (int) (m << 2);
+    int cs = (active ? count : 0) | (int) (m << 4);
     if (!active) {
-        // static bodies are brought to rest (src/rigid_body.c:339-347); nothing else happens
-        const int ta = __float_as_int(w.mprop[b.x].w) & 0xff, tb = __float_as_int(w.mprop[b.y].w) & 0xff;
-        if (ta == FX_BODY_STATIC) vel[b.x - lo] = make_float4(0.f, 0.f, 0.f, va4.w);
-        if (tb == FX_BODY_STATIC) vel[b.y - lo] = make_float4(0.f, 0.f, 0.f, vb4.w);
-        return;
+        if ((__float_as_int(mpa.w) & 0xff) == FX_BODY_STATIC) cs |= CS_ZERO_A;
+        if ((__float_as_int(mpb.w) & 0xff) == FX_BODY_STATIC) cs |= CS_ZERO_B;
     }
-    Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
+    q.b = b;
+    q.cs = cs;
+    q.nt = make_float4(n.x, n.y, t.x, t.y);
+    q.mat = make_float4(hdr.z, hdr.w, inv_ia, inv_ib);
+    q.r[0] = q.r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.lam[0] = q.lam[1] = make_float2(0.f, 0.f);
+    w.sol.body[s] = b;
+    w.sol.nt[s] = q.nt;
+    w.sol.mat[s] = q.mat;
+    w.sol.count_src[s] = cs;
+    if (!active) return q;
     for (int c = 0; c < count; ++c) {
         const float4 g = man.geo[2 * m + c];
         const float4 im = man.imp[2 * m + c];
@@ -91,16 +121,61 @@ __device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const 
         contact_arms(k, v2(g.x, g.y), v2(pa4.x, pa4.y), v2(pb4.x, pb4.y));
         k.bias = contact_bias(g.z, inv_dt);
         contact_masses(k, n, t, inv_ma, inv_mb, inv_ia, inv_ib);
-        contact_warm_start(k, n, t, im.y, im.w, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
-        w.sol.r[SOL_AT(w, s, c)] = make_float4(k.r1.x, k.r1.y, k.r2.x, k.r2.y);
+        q.r[c] = make_float4(k.r1.x, k.r1.y, k.r2.x, k.r2.y);
+        q.lam[c] = make_float2(im.y, im.w);
+        w.sol.r[SOL_AT(w, s, c)] = q.r[c];
         w.sol.u[SOL_AT(w, s, c)] = make_float4(k.u1.x, k.u1.y, k.u2.x, k.u2.y);
         w.sol.k[SOL_AT(w, s, c)] = make_float4(k.bias, k.nmass, k.tmass, 0.0f);
-        w.sol.lam[SOL_AT(w, s, c)] = make_float2(im.y, im.w);
+        w.sol.lam[SOL_AT(w, s, c)] = q.lam[c];
+    }
+    return q;
+}
+
+__device__ __forceinline__ WarmRec load_warm_record(const DevWorld &w, unsigned int s, int2 b, int cs) {
+    WarmRec q;
+    q.b = b;
+    q.cs = cs;
+    q.nt = w.sol.nt[s];
+    q.mat = w.sol.mat[s];
+    const int count = CS_COUNT(cs);
+    q.r[0] = q.r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    q.lam[0] = q.lam[1] = make_float2(0.f, 0.f);
+    if (count > 0) { q.r[0] = w.sol.r[SOL_AT(w, s, 0)]; q.lam[0] = w.sol.lam[SOL_AT(w, s, 0)]; }
+    if (count > 1) { q.r[1] = w.sol.r[SOL_AT(w, s, 1)]; q.lam[1] = w.sol.lam[SOL_AT(w, s, 1)]; }
+    return q;
+}
+
+// the warm start of one manifold (src/rigid_body.c:333-411) from its record
+template <class Vel>
+__device__ __forceinline__ void warm_start_apply(const WarmRec &q, const Vel &vel) {
+    const int count = CS_COUNT(q.cs);
+    if (count == 0) {
+        // static bodies are brought to rest (src/rigid_body.c:339-347); nothing else happens
+        if (q.cs & CS_ZERO_A) { const float4 v = vel.load(q.b.x); vel.store(q.b.x, make_float4(0.f, 0.f, 0.f, v.w)); }
+        if (q.cs & CS_ZERO_B) { const float4 v = vel.load(q.b.y); vel.store(q.b.y, make_float4(0.f, 0.f, 0.f, v.w)); }
+        return;
+    }
+    const float4 va4 = vel.load(q.b.x), vb4 = vel.load(q.b.y);
+    const float inv_ma = va4.w, inv_mb = vb4.w, inv_ia = q.mat.z, inv_ib = q.mat.w;
+    const V2 n = v2(q.nt.x, q.nt.y), t = v2(q.nt.z, q.nt.w);
+    Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
+    for (int c = 0; c < count; ++c) {
+        ContactK k;
+        k.r1 = v2(q.r[c].x, q.r[c].y);
+        k.r2 = v2(q.r[c].z, q.r[c].w);
+        contact_warm_start(k, n, t, q.lam[c].x, q.lam[c].y, inv_ma, inv_mb, inv_ia, inv_ib, va, vb);
     }
     // a body that cannot move is left alone: its value would not change, and thousands of manifolds of one
     // colour share a floor ([measured] 1 M circles on 8 floors: solve 6.5 ms with these stores)
-    if (inv_ma > 0.0f || inv_ia > 0.0f) vel[b.x - lo] = make_float4(va.x, va.y, va.w, inv_ma);
-    if (inv_mb > 0.0f || inv_ib > 0.0f) vel[b.y - lo] = make_float4(vb.x, vb.y, vb.w, inv_mb);
+    if (inv_ma > 0.0f || inv_ia > 0.0f) vel.store(q.b.x, make_float4(va.x, va.y, va.w, inv_ma));
+    if (inv_mb > 0.0f || inv_ib > 0.0f) vel.store(q.b.y, make_float4(vb.x, vb.y, vb.w, inv_mb));
+}
+
+template <class Vel>
+__device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const ManifoldSet &man, unsigned int m, unsigned int s,
+                                                       const Vel &vel, float inv_dt) {
+    const int2 b = man.body[m];
+    warm_start_apply(build_record(w, man, m, s, vel.load(b.x).w, vel.load(b.y).w, inv_dt), vel);
 }
 
 // what a sweep reads of a slot through the slot index alone ("level 1"); it does not depend on any velocity
@@ -110,22 +185,25 @@ struct SweepRec {
     float4 nt, mat, r0, u0, k0;
     float2 l0;
 };
-__device__ __forceinline__ SweepRec sweep_load(const DevWorld &w, unsigned int s) {
+__device__ __forceinline__ SweepRec sweep_load_rest(const DevWorld &w, unsigned int s, int2 b, int cs) {
     SweepRec q;
-    q.cs = w.sol.count_src[s];
-    q.b = w.sol.body[s];
+    q.cs = cs;
+    q.b = b;
     q.nt = w.sol.nt[s];
     q.mat = w.sol.mat[s];
     q.r0 = w.sol.r[SOL_AT(w, s, 0)]; q.u0 = w.sol.u[SOL_AT(w, s, 0)]; q.k0 = w.sol.k[SOL_AT(w, s, 0)];
     q.l0 = w.sol.lam[SOL_AT(w, s, 0)];
     return q;
 }
-__device__ __forceinline__ void sweep_apply(const DevWorld &w, unsigned int s, SweepRec q, float4 *vel, int lo) {
-    const int count = q.cs & 3;
-    if (count == 0) return;
+__device__ __forceinline__ SweepRec sweep_load(const DevWorld &w, unsigned int s) {
+    return sweep_load_rest(w, s, w.sol.body[s], w.sol.count_src[s]);
+}
+// one Gauss-Seidel update of the manifold at slot s; va4 / vb4: the velocities of its bodies as just loaded
+template <class Vel>
+__device__ __forceinline__ void sweep_apply(const DevWorld &w, unsigned int s, const SweepRec &q, float4 va4, float4 vb4, const Vel &vel) {
+    const int count = CS_COUNT(q.cs);
     // level 2: the velocities (addressed through b) and, for the few two-contact manifolds, the second record
     const int2 b = q.b;
-    float4 va4 = vel[b.x - lo], vb4 = vel[b.y - lo];
     float4 r1 = q.r0, u1 = q.u0, k1 = q.k0;
     float2 l0 = q.l0, l1 = q.l0;
     if (count > 1) {
@@ -145,13 +223,16 @@ __device__ __forceinline__ void sweep_apply(const DevWorld &w, unsigned int s, S
         k.bias = k1.x; k.nmass = k1.y; k.tmass = k1.z;
         contact_resolve(k, n, t, q.mat.x, q.mat.y, l1.x, l1.y, va4.w, vb4.w, q.mat.z, q.mat.w, va, vb);
     }
-    if (va4.w > 0.0f || q.mat.z > 0.0f) vel[b.x - lo] = make_float4(va.x, va.y, va.w, va4.w);     // movable bodies only
-    if (vb4.w > 0.0f || q.mat.w > 0.0f) vel[b.y - lo] = make_float4(vb.x, vb.y, vb.w, vb4.w);
+    if (va4.w > 0.0f || q.mat.z > 0.0f) vel.store(b.x, make_float4(va.x, va.y, va.w, va4.w));     // movable bodies only
+    if (vb4.w > 0.0f || q.mat.w > 0.0f) vel.store(b.y, make_float4(vb.x, vb.y, vb.w, vb4.w));
     w.sol.lam[SOL_AT(w, s, 0)] = l0;
     if (count > 1) w.sol.lam[SOL_AT(w, s, 1)] = l1;
 }
-__device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, float4 *vel, int lo) {
-    sweep_apply(w, s, sweep_load(w, s), vel, lo);
+template <class Vel>
+__device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, const Vel &vel) {
+    const SweepRec q = sweep_load(w, s);
+    if (CS_COUNT(q.cs) == 0) return;
+    sweep_apply(w, s, q, vel.load(q.b.x), vel.load(q.b.y), vel);
 }
 
 // `phases`: bit 0 = colouring + ordering + solver records + warm start, bit 1 = `iterations` sweeps,
@@ -160,6 +241,7 @@ __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, flo
 #define SV_SETUP 1
 #define SV_SWEEP 2
 #define SV_WRITEBACK 4
+#define SV_RECORDS_ONLY 8     // with SV_SETUP: colouring, ordering and the solver records, but no warm start (k_sweep_cluster follows)
 // Two builds of the same kernel: MINB = 1 may use 128 registers (96 used, no spills; one block per SM: the
 // latency-bound small-world case), MINB = 2 is held to 64 registers so that two blocks fit an SM (large worlds
 // want the threads).  [measured] solve at 65k bodies 0.323 (MINB 1) vs 0.330 ms; at 1 M bodies 2.46 vs 2.27 ms.
@@ -316,10 +398,20 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     }
     grid.sync();
 
+    const VelArray gvel = { w.vel, 0 };
+    if (phases & SV_RECORDS_ONLY) {
+        // the records depend on positions only: one pass over all slots, no barrier; the cluster kernel warm-starts
+        for (unsigned int s = tid; s < M; s += nth) {
+            const unsigned int m = w.order[s];
+            const int2 b = man.body[m];
+            build_record(w, man, m, s, w.vel[b.x].w, w.vel[b.y].w, inv_dt);
+        }
+        return;
+    }
     // ---- phase 3: solver records + warm start, one colour at a time
     for (unsigned int c = 0; c < s_ncolors; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
-        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, w.vel, 0, inv_dt);
+        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, gvel, inv_dt);
         grid.sync();
     }
     } else {
@@ -329,6 +421,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
         __syncthreads();
     }
     const unsigned int ncolors = s_ncolors;
+    const VelArray gvel2 = { w.vel, 0 };
     // ---- phase 4: Gauss-Seidel sweeps
     // ([measured] fetching the next colour's records BEFORE the barrier -- software pipelining across grid.sync() --
     // was bit-identical and slower: solve 0.313 -> 0.432 ms at 65k bodies; the barrier's fence waits for the loads)
@@ -336,15 +429,15 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     for (int it = 0; it < iterations; ++it)
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
-            for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one(w, s, w.vel, 0);
+            for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one(w, s, gvel2);
             grid.sync();
         }
     // ---- phase 5: write the impulses and effective masses back to the cache
     if (phases & SV_WRITEBACK)
     for (unsigned int s = tid; s < M; s += nth) {
         const int cs = w.sol.count_src[s];
-        const unsigned int m = (unsigned int) cs >> 2;
-        const int count = cs & 3;
+        const unsigned int m = CS_SRC(cs);
+        const int count = CS_COUNT(cs);
         for (int c = 0; c < count; ++c) {
             float4 kk = w.sol.k[SOL_AT(w, s, c)];
             float2 lam = w.sol.lam[SOL_AT(w, s, c)];
@@ -507,21 +600,22 @@ __global__ void k_solve_local(DevWorld w, int iterations, int max_bodies) {
         __syncthreads();
         // ---- solver records + warm start, then the sweeps: block barriers only
         const unsigned int ncolors = s_ncolors;
+        const VelArray lvel = { svel, lo };
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
-            for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, svel, lo, inv_dt);
+            for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, lvel, inv_dt);
             __syncthreads();
         }
         for (int it = 0; it < iterations; ++it)
             for (unsigned int c = 0; c < ncolors; ++c) {
                 if (s_off[c] == s_off[c + 1]) continue;
-                for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) sweep_one(w, s, svel, lo);
+                for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) sweep_one(w, s, lvel);
                 __syncthreads();
             }
         for (unsigned int s = mbase + tid; s < mbase + mc; s += nth) {
             const int cs = w.sol.count_src[s];
-            const unsigned int m = (unsigned int) cs >> 2;
-            const int count = cs & 3;
+            const unsigned int m = CS_SRC(cs);
+            const int count = CS_COUNT(cs);
             for (int c = 0; c < count; ++c) {
                 const float4 kk = w.sol.k[SOL_AT(w, s, c)];
                 const float2 lam = w.sol.lam[SOL_AT(w, s, c)];
@@ -708,11 +802,218 @@ __global__ void k_solve_serial(DevWorld w, SerialOrder o, int iterations) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Cluster solve (sm_100a thread-block clusters + distributed shared memory + bulk async copies).
+//
+// A mid-size world (config 2: 65 k bodies, 124 k manifolds) is bound by its ~100 DEPENDENT colour phases, not by
+// bytes: in k_solve_colored every phase pays a grid-wide barrier over 148 SMs (~1.5 us), a record fetch and a
+// scattered velocity gather through L2, and a store drain -- 2.9 us per phase, 9 % of the HBM roofline.  Here the
+// warm start and the sweeps of the WHOLE world run inside ONE thread-block cluster (16 CTAs = 16 SMs on one GPC):
+//   * every body's velocity lives in the cluster's distributed shared memory for the whole solve (body i in CTA
+//     i mod 16, slot i / 16): the gathers and scatters of a phase are DSMEM accesses (~215 cycles, no L2 queueing);
+//   * phases are separated by the hardware cluster barrier (barrier.cluster.arrive.release / wait.acquire, ~380
+//     cycles) instead of a grid barrier;
+//   * the body indices of the NEXT phase's manifolds -- the head of the dependent chain -- are prefetched into a
+//     3-stage shared-memory ring by bulk async copies (cp.async.bulk + mbarrier complete_tx), which no barrier
+//     fence waits for; the rest of a record (position-only constants, 80 B) is fetched with coalesced loads that
+//     overlap the DSMEM gather.
+// Same colours, same phase order, same per-contact arithmetic (the templates above) as k_solve_colored: the two
+// kernels produce identical bits (tests/test_gpu_cluster.py).  The colouring, the ordering and the records are
+// built by k_solve_colored(SV_SETUP | SV_RECORDS_ONLY) on the full grid just before.
+// ---------------------------------------------------------------------------------------------
+#define CL_BLOCK 1024
+#define CL_STAGES 3
+#define CL_PAD 8
+#define CL_STAGE_ELEMS (CL_BLOCK + CL_PAD)
+#define CL_FIXED_SMEM (128 + CL_STAGES * CL_STAGE_ELEMS * (sizeof(int2) + sizeof(int)))
+
+__device__ __forceinline__ unsigned int cl_smem_addr(const void *p) { return (unsigned int) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cl_mbar_init(unsigned long long *bar, unsigned int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cl_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void cl_mbar_expect_tx(unsigned long long *bar, unsigned int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cl_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool cl_mbar_try_wait(unsigned long long *bar, unsigned int parity) {
+    unsigned int ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(cl_smem_addr(bar)), "r"(parity) : "memory");
+    return ok != 0u;
+}
+// bulk async copy global -> this CTA's shared memory, completion counted in bytes on `bar` (SASS: UBLKCP)
+__device__ __forceinline__ void cl_bulk_load(void *dst_smem, const void *src_gmem, unsigned int bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(cl_smem_addr(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(cl_smem_addr(bar)) : "memory");
+}
+
+// velocities in the cluster's distributed shared memory: body i -> CTA (i & mask), slot (i >> shift)
+struct ClusterVel {
+    float4 *base;                 // this CTA's slots
+    unsigned int mask, shift;
+    __device__ __forceinline__ float4 *at(int i) const {
+        return cg::this_cluster().map_shared_rank(base, (unsigned int) i & mask) + ((unsigned int) i >> shift);
+    }
+    __device__ __forceinline__ float4 load(int i) const { return *at(i); }
+    __device__ __forceinline__ void store(int i, float4 v) const { *at(i) = v; }
+};
+
+// CTA `rank` of `cs` takes slots [a, b) of colour c
+__device__ __forceinline__ void cl_subrange(const unsigned int *s_off, unsigned int c, unsigned int rank, unsigned int cs, unsigned int &a,
+                                            unsigned int &b) {
+    const unsigned int first = s_off[c], len = s_off[c + 1] - first, per = (len + cs - 1u) / cs;
+    a = first + min(len, rank * per);
+    b = first + min(len, (rank + 1u) * per);
+}
+
+__global__ void __launch_bounds__(CL_BLOCK, 1) k_sweep_cluster(DevWorld w, int iterations) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned int CS = cluster.num_blocks(), rank = cluster.block_rank(), tid = threadIdx.x;
+    extern __shared__ __align__(128) unsigned char cl_smem[];
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(cl_smem);                  // [CL_STAGES]
+    int2 *sbody = reinterpret_cast<int2 *>(cl_smem + 128);                                        // [CL_STAGES][CL_STAGE_ELEMS]
+    int *scs = reinterpret_cast<int *>(sbody + CL_STAGES * CL_STAGE_ELEMS);                       // [CL_STAGES][CL_STAGE_ELEMS]
+    float4 *svel = reinterpret_cast<float4 *>(scs + CL_STAGES * CL_STAGE_ELEMS);                  // [ceil(n / CS)]
+    __shared__ unsigned int s_off[FX_MAX_COLORS + 1];
+    const ManifoldSet man = w.man[*w.cur_flip];
+    const unsigned int M = w.ctr->n_manifolds, ncolors = w.ctr->n_colors;
+    const unsigned int n = (unsigned int) w.n, per = (n + CS - 1u) / CS;
+    const ClusterVel vel = { svel, CS - 1u, 31u - (unsigned int) __clz((int) CS) };
+
+    if (tid <= FX_MAX_COLORS) s_off[tid] = w.color_off[tid];
+    if (tid == 0)
+        for (int k = 0; k < CL_STAGES; ++k) cl_mbar_init(&bars[k], 1u);
+    for (unsigned int l = tid; l < per; l += CL_BLOCK) {
+        const unsigned int i = l * CS + rank;
+        svel[l] = i < n ? w.vel[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    // ---- producer (thread 0): the body-index / count words of this CTA's next chunks, CL_STAGES - 1 chunks ahead
+    int p_it = -1;
+    unsigned int p_c = 0u, p_k = 0u, p_issued = 0u;
+    auto issue_next = [&]() {
+        while (p_it < iterations) {
+            if (p_c >= ncolors) { p_c = 0u; ++p_it; continue; }
+            unsigned int a, b;
+            cl_subrange(s_off, p_c, rank, CS, a, b);
+            const unsigned int ak = a + p_k * CL_BLOCK;
+            if (ak >= b) { ++p_c; p_k = 0u; continue; }
+            const unsigned int bk = min(b, ak + CL_BLOCK), a4 = ak & ~3u, cnt4 = (bk - a4 + 3u) & ~3u;
+            const unsigned int stage = p_issued % CL_STAGES;
+            unsigned long long *bar = &bars[stage];
+            cl_mbar_expect_tx(bar, cnt4 * (unsigned int) (sizeof(int2) + sizeof(int)));
+            cl_bulk_load(sbody + stage * CL_STAGE_ELEMS, w.sol.body + a4, cnt4 * (unsigned int) sizeof(int2), bar);
+            cl_bulk_load(scs + stage * CL_STAGE_ELEMS, w.sol.count_src + a4, cnt4 * (unsigned int) sizeof(int), bar);
+            ++p_issued;
+            ++p_k;
+            return;
+        }
+    };
+    if (tid == 0)
+        for (int k = 0; k < CL_STAGES; ++k) issue_next();
+    cluster.sync();                       // every CTA's velocities are staged before anyone gathers
+
+    // ---- phases: warm start (it = -1), then `iterations` sweeps; one cluster barrier per non-empty colour
+    unsigned int consumed = 0u;
+    for (int it = -1; it < iterations; ++it)
+        for (unsigned int c = 0; c < ncolors; ++c) {
+            if (s_off[c] == s_off[c + 1]) continue;               // an emptied colour: no work, no barrier (uniform)
+            unsigned int a, b;
+            cl_subrange(s_off, c, rank, CS, a, b);
+            for (unsigned int ak = a; ak < b; ak += CL_BLOCK) {
+                const unsigned int bk = min(b, ak + CL_BLOCK), a4 = ak & ~3u;
+                const unsigned int stage = consumed % CL_STAGES, parity = (consumed / CL_STAGES) & 1u;
+                while (!cl_mbar_try_wait(&bars[stage], parity)) { }
+                const unsigned int s = ak + tid;
+                const bool valid = s < bk;
+                int2 body = make_int2(0, 0);
+                int cs = 0;
+                if (valid) {
+                    body = sbody[stage * CL_STAGE_ELEMS + (s - a4)];
+                    cs = scs[stage * CL_STAGE_ELEMS + (s - a4)];
+                }
+                __syncthreads();                                  // every thread holds its words: the stage may be refilled
+                if (tid == 0) issue_next();
+                ++consumed;
+                if (!valid) continue;
+                if (it < 0) {
+                    warm_start_apply(load_warm_record(w, s, body, cs), vel);
+                } else if (CS_COUNT(cs) != 0) {
+                    float4 *pa = vel.at(body.x), *pb = vel.at(body.y);
+                    const float4 va4 = *pa, vb4 = *pb;            // DSMEM gathers in flight while the record streams in from L2
+                    const SweepRec q = sweep_load_rest(w, s, body, cs);
+                    sweep_apply(w, s, q, va4, vb4, vel);
+                }
+            }
+            cluster.sync();
+        }
+
+    // ---- velocities back to the world array, impulses and effective masses back to the cache
+    for (unsigned int l = tid; l < per; l += CL_BLOCK) {
+        const unsigned int i = l * CS + rank;
+        if (i < n) w.vel[i] = svel[l];
+    }
+    for (unsigned int s = rank * CL_BLOCK + tid; s < M; s += CS * CL_BLOCK) {
+        const int cs = w.sol.count_src[s];
+        const unsigned int m = CS_SRC(cs);
+        const int count = CS_COUNT(cs);
+        for (int c = 0; c < count; ++c) {
+            const float4 kk = w.sol.k[SOL_AT(w, s, c)];
+            const float2 lam = w.sol.lam[SOL_AT(w, s, c)];
+            man.imp[2 * m + c] = make_float4(kk.y, lam.x, kk.z, lam.y);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // launch surface
 // ---------------------------------------------------------------------------------------------
 // the shared-memory opt-in is a per-DEVICE function attribute: set when a world is created on a device
 void fx_init_solver_attributes() {
     cudaFuncSetAttribute(k_solve_local, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_LOCAL_MAX_BODIES * 36);
+    cudaFuncSetAttribute(k_sweep_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    cudaFuncSetAttribute(k_sweep_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, FX_CLUSTER_MAX_SMEM);
+    (void) cudaGetLastError();
+}
+
+// Largest cluster (16, else 8 CTAs) that can hold `bodies` velocities in its distributed shared memory AND is
+// launchable on the current device; 0: the world does not fit (k_solve_colored takes it).
+int fx_cluster_size_for(int bodies) {
+    static const int pin = [] { const char *e = std::getenv("FEROX_CLUSTER"); return e ? std::atoi(e) : -1; }();   // 0: off, 8 / 16: pin the size
+    if (pin == 0 || bodies <= 0) return 0;
+    for (int cs = 16; cs >= 8; cs >>= 1) {
+        if (pin > 0 && cs != pin) continue;
+        const size_t smem = CL_FIXED_SMEM + (size_t) ((bodies + cs - 1) / cs) * sizeof(float4);
+        if (smem > FX_CLUSTER_MAX_SMEM) continue;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned int) cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.gridDim = dim3((unsigned int) cs); cfg.blockDim = dim3(CL_BLOCK); cfg.dynamicSmemBytes = smem;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, k_sweep_cluster, &cfg) == cudaSuccess && clusters >= 1) return cs;
+        (void) cudaGetLastError();
+    }
+    return 0;
+}
+
+void fx_launch_solve_cluster(const DevWorld &w, const FxLaunchCtx &cx, int iterations, long long work_hint, int cluster_size) {
+    // colouring, ordering and solver records on the full grid ...
+    fx_launch_solve_colored(w, cx, 0, work_hint, SV_SETUP | SV_RECORDS_ONLY);
+    // ... warm start, sweeps and write-back inside one cluster
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned int) cluster_size; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned int) cluster_size);
+    cfg.blockDim = dim3(CL_BLOCK);
+    cfg.dynamicSmemBytes = CL_FIXED_SMEM + (size_t) ((w.n + cluster_size - 1) / cluster_size) * sizeof(float4);
+    cfg.stream = cx.stream;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_sweep_cluster, w, iterations);
+    ++g_fx_launches;
 }
 
 int fx_query_coop_blocks(int device) {

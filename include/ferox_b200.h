@@ -336,6 +336,10 @@ long long frxGetLaunchCount(void);
 /* steps of this world that were served by replaying the captured CUDA graph of the launch sequence (the graph
    survives changes of dt and of the world clock: frUpdateWorld replays it call after call) */
 long long frxGetGraphReplays(const frWorld *w);
+/* which kernel solved the last production-mode step: 0 = k_solve_colored on the whole grid (large worlds, strips),
+   -1 = k_solve_local (one CTA per sub-world / small world), 8 or 16 = k_sweep_cluster in one thread-block cluster of
+   that many CTAs (mid-size worlds; FEROX_CLUSTER=0 disables it, FEROX_CLUSTER=8|16 pins the size) */
+int frxGetWorldSolverKernel(const frWorld *w);
 /* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture a span */
 void frxProfilerRange(int start);
 /* n frStepWorld calls, each bracketed by its own CUDA-event pair on the world's stream; with flushL2
