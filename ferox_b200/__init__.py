@@ -78,6 +78,7 @@ EXT_PROTOTYPES = {
     "frxGetLaunchCount": (C.c_longlong, []),
     "frxGetGraphReplays": (C.c_longlong, [P]),
     "frxGetWorldSolverKernel": (I, [P]),
+    "frxGetColorHistogram": (I, [P, i32p]),
     "frxProfilerRange": (None, [I]),
     "frxTimedSteps": (I, [P, F, I, I, f32p]),
 }

@@ -979,8 +979,12 @@ void fx_init_solver_attributes() {
 // Largest cluster (16, else 8 CTAs) that can hold `bodies` velocities in its distributed shared memory AND is
 // launchable on the current device; 0: the world does not fit (k_solve_colored takes it).
 int fx_cluster_size_for(int bodies) {
-    static const int pin = [] { const char *e = std::getenv("FEROX_CLUSTER"); return e ? std::atoi(e) : -1; }();   // 0: off, 8 / 16: pin the size
-    if (pin == 0 || bodies <= 0) return 0;
+    // opt-in (FEROX_CLUSTER=8|16): [measured, B200] bit-identical to the grid solver but SLOWER at every size it fits --
+    // config 2: solve 0.685 ms in a 16-CTA cluster, 1.07 ms in 8 CTAs, 0.296 ms on the grid: sixteen SMs issue the
+    // ~430 warp instructions per manifold update 9x slower than 148 do, and DSMEM gathers (~20 B/cycle per SM) are a
+    // throughput path, not a latency path (profiles/r02_cluster_v1_*)
+    static const int pin = [] { const char *e = std::getenv("FEROX_CLUSTER"); return e ? std::atoi(e) : 0; }();   // 0: off, 8 / 16: pin the size
+    if (pin <= 0 || bodies <= 0) return 0;
     for (int cs = 16; cs >= 8; cs >>= 1) {
         if (pin > 0 && cs != pin) continue;
         const size_t smem = CL_FIXED_SMEM + (size_t) ((bodies + cs - 1) / cs) * sizeof(float4);

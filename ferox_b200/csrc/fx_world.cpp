@@ -885,7 +885,7 @@ static void step_once(frWorld *w, float dt) {
     if (w->cluster_bodies != d.n) {
         static const int cluster_max = [] { const char *e = std::getenv("FEROX_CLUSTER_MAX_BODIES"); return e ? std::atoi(e) : 131072; }();
         w->cluster_bodies = d.n;
-        w->cluster_size = (!w->force_large && d.n <= cluster_max) ? fx_cluster_size_for(d.n) : 0;
+        w->cluster_size = (!w->force_large && d.n <= cluster_max) ? fx_cluster_size_for(d.n) : 0;   // 0 unless FEROX_CLUSTER=8|16
     }
     const int coop_blocks = fx_solve_colored_blocks(w->cx, hint) + (w->cluster_size << 20);   // (part of the graph key)
     // ---- fast path: replay the captured launch sequence ----
@@ -1009,6 +1009,19 @@ extern "C" float frxEventElapsedMs(frWorld *w, int from, int to) {
 }
 extern "C" long long frxGetLaunchCount(void) { return g_fx_launches; }
 extern "C" long long frxGetGraphReplays(const frWorld *w) { return w ? w->graph_replays : 0; }
+extern "C" int frxGetColorHistogram(frWorld *w, int *out64) {
+    if (!w || !w->device_ok || !out64) return 0;
+    cudaSetDevice(w->device);
+    unsigned int off[FX_MAX_COLORS + 1];
+    cudaMemcpyAsync(off, w->dw.color_off, sizeof off, cudaMemcpyDeviceToHost, w->stream);
+    if (!fx_cuda_ok(cudaStreamSynchronize(w->stream), "colour histogram")) return 0;
+    int n = 0;
+    for (int c = 0; c < FX_MAX_COLORS; ++c) {
+        out64[c] = (int) (off[c + 1] - off[c]);
+        if (out64[c] > 0) n = c + 1;
+    }
+    return n;
+}
 extern "C" int frxGetWorldSolverKernel(const frWorld *w) {
     if (!w) return 0;
     if (w->use_local && w->local_max_bodies > 0) return -1;

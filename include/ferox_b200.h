@@ -340,6 +340,8 @@ long long frxGetGraphReplays(const frWorld *w);
    -1 = k_solve_local (one CTA per sub-world / small world), 8 or 16 = k_sweep_cluster in one thread-block cluster of
    that many CTAs (mid-size worlds; FEROX_CLUSTER=0 disables it, FEROX_CLUSTER=8|16 pins the size) */
 int frxGetWorldSolverKernel(const frWorld *w);
+/* manifolds per colour of the last production-mode step: out[c] for c < 64; returns the number of colours */
+int frxGetColorHistogram(frWorld *w, int *out64);
 /* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture a span */
 void frxProfilerRange(int start);
 /* n frStepWorld calls, each bracketed by its own CUDA-event pair on the world's stream; with flushL2
