@@ -10,6 +10,8 @@
 extern long long g_fx_launches;
 #include "fx_narrow.cuh"
 #include "fx_solver.cuh"
+#include "fx_raycast.cuh"
+#include "fx_scan.cuh"
 
 #define BD_BLOCK 256
 
@@ -183,6 +185,74 @@ __global__ void k_sincos(const float *a, int n, float *s, float *c) {
         s[i] = r.s;
         c[i] = r.c;
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// world ray casts on the device state (reference src/world.c:291-320 + src/broad_phase.c:130-179)
+//
+// The reference re-inserts every body into the spatial hash, queries the ray's bounding box and casts the ray
+// against every body found, in ascending index order.  A body is found iff its inclusive cell rectangle
+// intersects the box's (App. A.2), so the same visiting set and order come out of ONE ordered sweep over the
+// bodies: a block per ray, 256 bodies per round, the ray test on the bodies whose rectangle matches, hits
+// compacted in index order.  Thousands of rays (the sensor fans of batched RL worlds) go in one launch.
+// ---------------------------------------------------------------------------------------------
+#define RC_BLOCK 256
+struct RayDev {
+    V2 origin, direction;
+    float max_distance;
+};
+static_assert(sizeof(RayDev) == 20, "frRay layout");
+
+__global__ void __launch_bounds__(RC_BLOCK) k_raycast_batch(DevWorld w, const RayDev *rays, int nrays, int max_hits, RayHitPod *hits, int *counts) {
+    __shared__ unsigned int s_run;
+    for (int r = blockIdx.x; r < nrays; r += gridDim.x) {
+        const RayDev ray = rays[r];
+        const V2 o = ray.origin, dir = vunit(ray.direction);
+        const V2 e = vadd(o, vscale(dir, ray.max_distance));
+        // the query box of src/world.c:311-314 and its cell rectangle (src/broad_phase.c:138-142)
+        const float bx = pin_fminf(o.x, e.x), by = pin_fminf(o.y, e.y), bw = fabsf(e.x - o.x), bh = fabsf(e.y - o.y);
+        const int qx0 = cell_coord(bx, w.inv_cell), qy0 = cell_coord(by, w.inv_cell);
+        const int qx1 = cell_coord(bx + bw, w.inv_cell), qy1 = cell_coord(by + bh, w.inv_cell);
+        if (threadIdx.x == 0) s_run = 0u;
+        __syncthreads();
+        for (int base = 0; base < w.n_owned; base += RC_BLOCK) {
+            const int i = base + (int) threadIdx.x;
+            bool found = false;
+            RayHitPod hit;
+            memset(&hit, 0, sizeof hit);
+            if (i < w.n_owned) {
+                const float4 a = w.aabb[i];
+                const int x0 = cell_coord(a.x, w.inv_cell), y0 = cell_coord(a.y, w.inv_cell);
+                const int x1 = cell_coord(a.x + a.z, w.inv_cell), y1 = cell_coord(a.y + a.w, w.inv_cell);
+                if (x0 <= qx1 && qx0 <= x1 && y0 <= qy1 && qy0 <= y1) {
+                    const int2 sh = w.shape[i];
+                    if (sh.x >= 0) {
+                        const ShapeDev *s = &w.shapes[sh.x];
+                        const float4 p = w.posrot[i];
+                        Xf t;
+                        t.p = v2(p.x, p.y); t.sn = p.z; t.cs = p.w;
+                        found = ray_vs_shape(s->type, s->radius, s->nv, s->verts, t, o, dir, ray.max_distance, hit);
+                        hit.body = i;
+                    }
+                }
+            }
+            unsigned int total;
+            const unsigned int excl = block_exclusive_scan<RC_BLOCK>(found ? 1u : 0u, &total);
+            const unsigned int pos = s_run + excl;
+            if (found && (int) pos < max_hits) hits[(size_t) r * (size_t) max_hits + pos] = hit;
+            __syncthreads();
+            if (threadIdx.x == 0) s_run += total;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) counts[r] = (int) s_run;
+        __syncthreads();
+    }
+}
+
+void fx_launch_raycast_batch(const DevWorld &w, const FxLaunchCtx &cx, const void *rays, int nrays, int max_hits, void *hits, int *counts) {
+    if (nrays <= 0) return;
+    k_raycast_batch<<<nrays < cx.max_blocks ? nrays : cx.max_blocks, RC_BLOCK, 0, cx.stream>>>(w, (const RayDev *) rays, nrays, max_hits, (RayHitPod *) hits, counts);
+    ++g_fx_launches;
 }
 
 void fx_launch_single_body(const DevWorld &w, cudaStream_t s, int i, int op, float dt) { k_single_body<<<1, 32, 0, s>>>(w, i, op, dt); ++g_fx_launches; }

@@ -52,6 +52,12 @@ struct CollisionPod {
     float friction, restitution;
 };
 static_assert(sizeof(CollisionPod) == 92, "frCollision layout");
+// one record of the collision-handler bridge = include/ferox_b200.h frxManifold
+struct ManifoldRec {
+    int first, second;
+    CollisionPod value;
+};
+static_assert(sizeof(ManifoldRec) == 100, "frxManifold layout");
 
 // what the narrow phase produces for one pair (the part of frCollision it writes)
 struct Manifold {

@@ -82,6 +82,7 @@ struct frWorld_ {
     float accumulator = 0.f, timestamp = 0.f;
     frCollisionHandler handler{ nullptr, nullptr };
     int solver_mode = FRX_SOLVER_COLORED;
+    void *bridge = nullptr;              // collision-handler bridge buffers (fx_world.cpp HandlerBridge)
     void *mh_cache = nullptr;            // pinned host copy of the manifold arrays (handlers, frxGetManifolds)
     int n_groups = 1;                // > 1: a batch of independent sub-worlds sharing this pipeline
     int *d_group = nullptr;

@@ -78,6 +78,14 @@ void fx_launch_finish_step(const DevWorld &w, const FxLaunchCtx &cx);
 int fx_query_coop_blocks(int device);
 void fx_launch_rehash_prev(const DevWorld &w, const FxLaunchCtx &cx);
 void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o);
+// collision-handler bridge: live manifolds <-> packed public records, in visiting order (idx: reference-order mode)
+void fx_launch_visit_index(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, unsigned int *idx, unsigned int cap);
+void fx_launch_pack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, ManifoldRec *out);
+void fx_launch_unpack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, const ManifoldRec *in);
+
+// world ray casts on the device state (fx_bodies.cu): rays = frRay[nrays], hits = frRaycastHit[nrays][max_hits] with the world
+// index in the body slot, counts[r] = hits found for ray r (may exceed max_hits)
+void fx_launch_raycast_batch(const DevWorld &w, const FxLaunchCtx &cx, const void *rays, int nrays, int max_hits, void *hits, int *counts);
 
 // single-pair / utility entry points (used by the public per-body functions and the tests)
 void fx_launch_collide_pairs(const DevWorld &w, const FxLaunchCtx &cx, const int2 *pairs, int n, Manifold *out);

@@ -15,6 +15,7 @@
 #include <new>
 
 #include "fx_host.h"
+#include "fx_raycast.cuh"
 
 static uint64_t g_shape_epoch = 1;
 uint64_t fx_shape_epoch() { return g_shape_epoch; }
@@ -452,81 +453,33 @@ extern "C" void frApplyImpulseToBody(frBody *b, frVector2 point, frVector2 impul
 // ================================================================================================
 // ray casts and point queries (reference src/collision.c:138-220, 561-625; rigid_body.c:261-289)
 // ================================================================================================
-static bool hit_circle_line(V2 center, float radius, V2 origin, V2 dir, float *distance) {
-    V2 oc = vsub(center, origin);
-    float dot = vdot(oc, dir);
-    float h2 = vlen2(oc) - (dot * dot);
-    float b2 = (radius * radius) - h2;
-    *distance = dot - sqrtf(b2);
-    return (dot >= 0.0f && b2 >= 0.0f);
-}
-static bool hit_lines(V2 o1, V2 d1, V2 o2, V2 d2, float *distance) {
-    float rxs = vcross(d1, d2);
-    V2 qp = vsub(o2, o1);
-    float qpxs = vcross(qp, d2), qpxr = vcross(qp, d1);
-    if (rxs != 0.0f) {
-        float inv = 1.0f / rxs;
-        float t = qpxs * inv, u = qpxr * inv;
-        if ((t >= 0.0f && t <= 1.0f) && (u >= 0.0f && u <= 1.0f)) { *distance = t; return true; }
-        return false;
-    }
-    if (qpxr != 0.0f) return false;
-    float rdr = vdot(d1, d1), sdr = vdot(d2, d1);
-    float inv = 1.0f / rdr;
-    float qpdr = vdot(qp, d1);
-    float k, t0 = qpdr * inv, t1 = t0 + sdr * inv;
-    if (sdr < 0.0f) { k = t0; t0 = t1; t1 = k; }
-    if ((t0 < 0.0f && t1 == 0.0f) || (t0 == 1.0f && t1 > 1.0f)) { *distance = (t0 == 1.0f); return true; }
-    return (t1 >= 0.0f && t0 <= 1.0f);
-}
-
+// (the arithmetic lives in fx_raycast.cuh, shared with the device world-query kernel)
 extern "C" bool frComputeRaycast(const frBody *b, frRay ray, frRaycastHit *hit) {
     if (b == nullptr) return false;
-    V2 dir = vunit(V(ray.direction)), origin = V(ray.origin);
+    const V2 dir = vunit(V(ray.direction)), origin = V(ray.origin);
     const frShape *s = b->shape;
-    frTransform tx = frGetBodyTransform(b);
-    frShapeType type = frGetShapeType(s);
-    float distance = FLT_MAX;
-    if (type == FR_SHAPE_CIRCLE) {
-        (void) hit_circle_line(V(tx.position), s->radius, origin, dir, &distance);
-        bool result = (distance >= 0.0f) && (distance <= ray.maxDistance);
-        if (hit != nullptr) {
-            hit->body = const_cast<frBody *>(b);
-            hit->point = F(vadd(origin, vscale(dir, distance)));
-            hit->normal = F(vperp_left(vsub(origin, V(hit->point))));
-            hit->distance = distance;
-            hit->inside = (distance < 0.0f);
-        }
-        return result;
-    }
+    const frTransform tx = frGetBodyTransform(b);
+    const frShapeType type = frGetShapeType(s);
+    if (type != FR_SHAPE_CIRCLE && type != FR_SHAPE_POLYGON) return false;
+    RayHitPod pod;
+    std::memset(&pod, 0, sizeof pod);
+    if (hit != nullptr) { pod.point = V(hit->point); pod.normal = V(hit->normal); pod.distance = hit->distance; pod.inside = hit->inside ? 1 : 0; }
+    V2 verts[FX_MAX_VERTS] = {};
+    int nv = 0;
     if (type == FR_SHAPE_POLYGON) {
-        int crossings = 0;
-        float best = FLT_MAX;
-        Xf t = to_xf(tx);
-        const int n = s->vertices.count;
-        for (int j = n - 1, i = 0; i < n; j = i, ++i) {
-            V2 a = xf_apply(V(s->vertices.data[i]), t), c = xf_apply(V(s->vertices.data[j]), t);
-            V2 edge = vsub(a, c);
-            bool ok = hit_lines(origin, dir, c, edge, &distance);
-            if (ok && distance <= ray.maxDistance) {
-                if (best > distance) {
-                    best = distance;
-                    if (hit != nullptr) {
-                        hit->point = F(vadd(origin, vscale(dir, best)));
-                        hit->normal = F(vperp_left(edge));
-                    }
-                }
-                ++crossings;
-            }
-        }
-        bool inside = (crossings & 1) != 0;
-        if (hit != nullptr) {
-            hit->body = const_cast<frBody *>(b);
-            hit->inside = inside;
-        }
-        return (!inside && crossings > 0);
+        nv = s->vertices.count < FX_MAX_VERTS ? s->vertices.count : FX_MAX_VERTS;
+        for (int k = 0; k < nv; ++k) verts[k] = V(s->vertices.data[k]);
     }
-    return false;
+    const bool result = ray_vs_shape((int) type, s->radius, nv, verts, to_xf(tx), origin, dir, ray.maxDistance, pod);
+    if (hit != nullptr) {
+        // (pod started as *hit and only the fields the reference writes were touched)
+        hit->body = const_cast<frBody *>(b);
+        hit->point = F(pod.point);
+        hit->normal = F(pod.normal);
+        hit->distance = pod.distance;
+        hit->inside = pod.inside != 0;
+    }
+    return result;
 }
 
 extern "C" bool frBodyContainsPoint(const frBody *b, frVector2 point) {

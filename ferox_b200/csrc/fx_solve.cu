@@ -802,6 +802,105 @@ __global__ void k_solve_serial(DevWorld w, SerialOrder o, int iterations) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// collision-handler bridge (src/world.c:209-214, 254-259): the live manifolds as an array of the PUBLIC records
+// -- {first index, second index, frCollision} = 100 bytes, include/ferox_b200.h frxManifold -- in the order the
+// reference visits its cache array, packed on the device so that the host gets ONE contiguous download it can hand
+// to the callbacks in place, and takes ONE upload back (whatever the callbacks edited is in it).
+// ---------------------------------------------------------------------------------------------
+#define MB_BLOCK 128
+#define MB_WORDS 25     // sizeof(ManifoldRec) / 4
+static_assert(sizeof(ManifoldRec) == 4 * MB_WORDS, "frxManifold layout");
+
+// reference-order mode: dense index of every entry of the reference-order key array
+__global__ void __launch_bounds__(MB_BLOCK) k_visit_index(DevWorld w, SerialOrder o, unsigned int *idx) {
+    const unsigned int len = *o.r_len;
+    for (unsigned int r = blockIdx.x * blockDim.x + threadIdx.x; r < len; r += gridDim.x * blockDim.x) {
+        const int m = cache_lookup(w, o.r_key[r]);
+        idx[r] = m < 0 ? 0xffffffffu : (unsigned int) m;
+    }
+}
+
+__global__ void __launch_bounds__(MB_BLOCK) k_pack_collisions(DevWorld w, const unsigned int *idx, unsigned int n, ManifoldRec *out) {
+    __shared__ unsigned int s_rec[MB_BLOCK * MB_WORDS];       // odd record stride: conflict-free per-thread fills
+    const ManifoldSet man = w.man[*w.cur_flip];
+    for (unsigned int base = blockIdx.x * MB_BLOCK; base < n; base += gridDim.x * MB_BLOCK) {
+        const unsigned int r = base + threadIdx.x;
+        ManifoldRec rec;
+        memset(&rec, 0, sizeof rec);
+        rec.first = rec.second = -1;
+        const unsigned int m = r < n ? (idx ? idx[r] : r) : 0xffffffffu;
+        if (m != 0xffffffffu) {
+            const int2 b = man.body[m];
+            const float4 hdr = man.hdr[m];
+            rec.first = b.x; rec.second = b.y;
+            rec.value.count = man.meta[m].x;
+            rec.value.direction = v2(hdr.x, hdr.y);
+            rec.value.friction = hdr.z; rec.value.restitution = hdr.w;
+            for (int k = 0; k < 2; ++k) {
+                const float4 g = man.geo[2 * m + k], im = man.imp[2 * m + k];
+                ContactPod &ct = rec.value.contacts[k];
+                ct.id = man.cid[2 * m + k];
+                ct.point = v2(g.x, g.y); ct.depth = g.z; ct.timestamp = g.w;
+                ct.normalMass = im.x; ct.normalScalar = im.y; ct.tangentMass = im.z; ct.tangentScalar = im.w;
+            }
+        }
+        const unsigned int *src = reinterpret_cast<const unsigned int *>(&rec);
+#pragma unroll
+        for (int k = 0; k < MB_WORDS; ++k) s_rec[threadIdx.x * MB_WORDS + k] = src[k];
+        __syncthreads();
+        const unsigned int words = min(MB_BLOCK, n - base) * MB_WORDS;
+        unsigned int *dst = reinterpret_cast<unsigned int *>(out + base);
+        for (unsigned int t = threadIdx.x; t < words; t += MB_BLOCK) dst[t] = s_rec[t];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(MB_BLOCK) k_unpack_collisions(DevWorld w, const unsigned int *idx, unsigned int n, const ManifoldRec *in) {
+    __shared__ unsigned int s_rec[MB_BLOCK * MB_WORDS];
+    const ManifoldSet man = w.man[*w.cur_flip];
+    for (unsigned int base = blockIdx.x * MB_BLOCK; base < n; base += gridDim.x * MB_BLOCK) {
+        const unsigned int words = min(MB_BLOCK, n - base) * MB_WORDS;
+        const unsigned int *src = reinterpret_cast<const unsigned int *>(in + base);
+        for (unsigned int t = threadIdx.x; t < words; t += MB_BLOCK) s_rec[t] = src[t];
+        __syncthreads();
+        const unsigned int r = base + threadIdx.x;
+        const unsigned int m = r < n ? (idx ? idx[r] : r) : 0xffffffffu;
+        if (m != 0xffffffffu) {
+            ManifoldRec rec;
+            unsigned int *dst = reinterpret_cast<unsigned int *>(&rec);
+#pragma unroll
+            for (int k = 0; k < MB_WORDS; ++k) dst[k] = s_rec[threadIdx.x * MB_WORDS + k];
+            int2 meta = man.meta[m];
+            meta.x = rec.value.count < 0 ? 0 : (rec.value.count > 2 ? 2 : rec.value.count);
+            man.meta[m] = meta;
+            man.hdr[m] = make_float4(rec.value.direction.x, rec.value.direction.y, rec.value.friction, rec.value.restitution);
+            for (int k = 0; k < 2; ++k) {
+                const ContactPod &ct = rec.value.contacts[k];
+                man.cid[2 * m + k] = ct.id;
+                man.geo[2 * m + k] = make_float4(ct.point.x, ct.point.y, ct.depth, ct.timestamp);
+                man.imp[2 * m + k] = make_float4(ct.normalMass, ct.normalScalar, ct.tangentMass, ct.tangentScalar);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void fx_launch_visit_index(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, unsigned int *idx, unsigned int cap) {
+    long long g = ((long long) cap + MB_BLOCK - 1) / MB_BLOCK;
+    k_visit_index<<<(int) (g < 1 ? 1 : (g > cx.max_blocks ? cx.max_blocks : g)), MB_BLOCK, 0, cx.stream>>>(w, o, idx); ++g_fx_launches;
+}
+void fx_launch_pack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, ManifoldRec *out) {
+    if (n == 0) return;
+    long long g = ((long long) n + MB_BLOCK - 1) / MB_BLOCK;
+    k_pack_collisions<<<(int) (g > cx.max_blocks ? cx.max_blocks : g), MB_BLOCK, 0, cx.stream>>>(w, idx, n, out); ++g_fx_launches;
+}
+void fx_launch_unpack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, const ManifoldRec *in) {
+    if (n == 0) return;
+    long long g = ((long long) n + MB_BLOCK - 1) / MB_BLOCK;
+    k_unpack_collisions<<<(int) (g > cx.max_blocks ? cx.max_blocks : g), MB_BLOCK, 0, cx.stream>>>(w, idx, n, in); ++g_fx_launches;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Cluster solve (sm_100a thread-block clusters + distributed shared memory + bulk async copies).
 //
 // A mid-size world (config 2: 65 k bodies, 124 k manifolds) is bound by its ~100 DEPENDENT colour phases, not by

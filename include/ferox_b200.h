@@ -319,6 +319,13 @@ int frxGetCandidatePairs(frWorld *w, int *outTriples, int max);
 typedef struct frxManifold_ { int first, second; frCollision value; } frxManifold;   /* 100 B */
 int frxGetManifolds(frWorld *w, frxManifold *out, int max);
 
+/* World ray casts on the DEVICE state, many rays per call (the sensor path of batched RL worlds): for ray r up to
+   maxHitsPerRay hits are written to hits[r * maxHitsPerRay ...] in ascending world-index order -- exactly the
+   bodies, the order and the values frComputeWorldRaycast's callback would see for that ray (src/world.c:291-320) --
+   and counts[r] receives the number of hits found (it may exceed maxHitsPerRay: the rest were dropped).  Returns
+   the total number of hits found.  frComputeWorldRaycast itself runs through this path. */
+int frxRaycastBatch(frWorld *w, const frRay *rays, int nRays, frRaycastHit *hits, int *counts, int maxHitsPerRay);
+
 /* Batched narrow phase on bodies of a world: pairs[2*i], pairs[2*i+1] are world indices; out[i] is
    written only on a hit (like frComputeCollision); hit[i] receives 0/1.  Returns hits. */
 int frxComputeCollisions(frWorld *w, const int *pairs, int nPairs, frCollision *out, int *hit);

@@ -848,3 +848,67 @@ def test_mutating_handlers_forces_and_membership_match_reference(gpu, ref):
         assert rm == gm, "membership at step %d" % s
         assert_states_equal(rst, gst, "step %d" % s)
     assert any(e[0] == "pre" and e[4] > 0 and abs(e[5] - 0.125) < 1e-7 for e in rlog[len(rlog) // 2:])   # the friction edit stuck
+
+
+def test_world_raycast_batch_matches_reference_for_thousands_of_rays(gpu, ref):
+    """frxRaycastBatch (device sweep over the world's state, fx_bodies.cu k_raycast_batch) against the unmodified
+    reference's frComputeWorldRaycast, ray by ray: the same bodies in the same (ascending-index) order with the
+    same points, normals, distances and inside flags, bit for bit -- 3,000 rays through a settled mixed pile,
+    long and short, from outside and from inside bodies (the polygon branch only sees crossings within one unit of
+    the origin, src/collision.c:592-600, so many rays start next to a body)."""
+    import ctypes as C
+    L = gpu
+    spec = scenes.mixed_pile(400, width=40.0)
+    worlds = []
+    for lib in (ref, L):
+        sc = scenes.Scene(lib, spec, prime=False)
+        if lib is L:
+            lib.frxSetWorldSolverMode(sc.world, fb.SOLVER_SERIAL)
+        lib.frStepWorld(sc.world, DT)
+        sc.step(120)
+        worlds.append(sc)
+    rs, gs = worlds
+    assert_states_equal(rs.snapshot(), gs.snapshot(), "settled pile")
+    st = gs.snapshot()
+    rng = np.random.default_rng(5)
+    n_rays = 3000
+    rays = (capi.Ray * n_rays)()
+    for k in range(n_rays):
+        if k % 3 == 0:                               # from the box around the pile, any direction, long
+            o = (rng.uniform(-5, 45), rng.uniform(-30, 5))
+            dist = rng.uniform(5, 90)
+        else:                                        # next to (or inside) a body, short
+            c = st["pos"][rng.integers(3, spec.n)]
+            o = (c[0] + rng.normal() * 0.6, c[1] + rng.normal() * 0.6)
+            dist = rng.choice([0.3, 1.0, 2.5, 20.0])
+        a = rng.uniform(0, 2 * np.pi)
+        scale = rng.choice([1.0, 0.25, 7.0])         # un-normalised directions are normalised by the callee
+        rays[k] = capi.Ray(capi.Vector2(float(np.float32(o[0])), float(np.float32(o[1]))),
+                           capi.Vector2(float(np.float32(np.cos(a) * scale)), float(np.float32(np.sin(a) * scale))), float(np.float32(dist)))
+    max_hits = 64
+    hits = (capi.RaycastHit * (n_rays * max_hits))()
+    counts = np.zeros(n_rays, np.int32)
+    total = L.frxRaycastBatch(gs.world, C.byref(rays), n_rays, C.byref(hits), counts, max_hits)
+    fb.check_error(L)
+    assert total == int(counts.sum()) and counts.max() <= max_hits
+    f32 = lambda x: np.float32(x).tobytes()
+    n_hits = 0
+    for k in range(n_rays):
+        want = []
+        cb = capi.RaycastQueryFunc(lambda h, ctx: want.append((rs.index_of[h.body], f32(h.point.x), f32(h.point.y), f32(h.normal.x), f32(h.normal.y),
+                                                               f32(h.distance), bool(h.inside))))
+        ref.frComputeWorldRaycast(rs.world, rays[k], cb, None)
+        got = []
+        for j in range(counts[k]):
+            h = hits[k * max_hits + j]
+            got.append((gs.index_of[h.body], f32(h.point.x), f32(h.point.y), f32(h.normal.x), f32(h.normal.y), f32(h.distance), bool(h.inside)))
+        assert got == want, (k, got, want)
+        n_hits += len(want)
+    assert n_hits > 500, n_hits
+    # frComputeWorldRaycast of the product is the same path, one ray at a time
+    for k in range(0, n_rays, 97):
+        got = []
+        cb = capi.RaycastQueryFunc(lambda h, ctx: got.append(gs.index_of[h.body]))
+        L.frComputeWorldRaycast(gs.world, rays[k], cb, None)
+        assert len(got) == counts[k]
+    rs.release(); gs.release()
