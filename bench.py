@@ -391,7 +391,8 @@ def sub_config3_shallow(L, dt, bodies=1048576, steps=200):
     speed = np.linalg.norm(st["vel"], axis=1)
     out = {"workload": "config3_shallow: %d uniform circles (r 0.5) on 8 storeys x 16 lattice rows, walled, cell 2.0, dt 1/60, settled 600 "
                        "steps (per-step working set > 2 GB, far larger than the 126 MB L2)" % bodies,
-           "bodies": n, "steps": steps, "ms_per_step": float(ms.mean()), "hz": 1e3 / float(ms.mean()), "value": n * steps / (float(ms.sum()) * 1e-3),
+           "bodies": n, "steps": steps, "ms_per_step": float(ms.mean()), "ms_per_step_median": float(np.median(ms)), "ms_per_step_max": float(ms.max()),
+           "hz": 1e3 / float(ms.mean()), "value": n * steps / (float(ms.sum()) * 1e-3),
            "unit": UNIT, "stage_ms_per_step": stage, "counters": ctr, "gpu_launches": launches, "overflow": int(ctr["overflow"]),
            "mean_speed": float(speed.mean()), "max_speed": float(speed.max()),
            "roofline": solver_roofline(ctr, stage["solve"], "k_solve_colored", "r02_config3_top_kernels_ncu.csv"),
@@ -817,6 +818,7 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
             rec = {"workload": "config4: %d independent worlds x 256 bodies (252 dynamic mixed + floor + 2 walls + kinematic paddle), ONE batch "
                                "(one launch set per step for all worlds), settled 300 steps, L2 flushed between timed steps" % nw,
                    "bodies": n, "worlds": nw, "steps": steps, "ms_per_step": elapsed / steps, "value": n * steps / (elapsed * 1e-3), "unit": UNIT,
+                   "hz": 1e3 * steps / elapsed,
                    "world_steps_per_s": nw * steps / (elapsed * 1e-3), "stage_ms_per_step": stage, "counters": ctr, "gpu_launches": launches,
                    "roofline": solver_roofline(ctr, stage["solve"], "k_solve_local (one CTA per sub-world, velocities in shared memory)")}
             if not args.no_cpu_baseline:

@@ -114,7 +114,9 @@ __device__ __forceinline__ WarmRec build_record(const DevWorld &w, const Manifol
     w.sol.mat[s] = q.mat;
     w.sol.count_src[s] = cs;
     if (!active) return q;
-    for (int c = 0; c < count; ++c) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {                      // (unrolled: q.r / q.lam stay in registers)
+        if (c >= count) break;
         const float4 g = man.geo[2 * m + c];
         const float4 im = man.imp[2 * m + c];
         ContactK k;
@@ -159,7 +161,9 @@ __device__ __forceinline__ void warm_start_apply(const WarmRec &q, const Vel &ve
     const float inv_ma = va4.w, inv_mb = vb4.w, inv_ia = q.mat.z, inv_ib = q.mat.w;
     const V2 n = v2(q.nt.x, q.nt.y), t = v2(q.nt.z, q.nt.w);
     Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
-    for (int c = 0; c < count; ++c) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+        if (c >= count) break;
         ContactK k;
         k.r1 = v2(q.r[c].x, q.r[c].y);
         k.r2 = v2(q.r[c].z, q.r[c].w);
@@ -233,6 +237,23 @@ __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, con
     const SweepRec q = sweep_load(w, s);
     if (CS_COUNT(q.cs) == 0) return;
     sweep_apply(w, s, q, vel.load(q.b.x), vel.load(q.b.y), vel);
+}
+
+// Tail colours.  A settled pile needs as many colours as its busiest body has contacts, but the last ones hold a
+// handful of manifolds ([measured] config 2: 25371, 23942, 22512, 20101, 16451, 10719, 1263, 33) while every colour
+// costs a grid barrier in every sweep.  The trailing colours that together hold at most `limit` manifolds are
+// therefore swept by block 0 alone, one after the other with block barriers, behind ONE grid barrier: same order on
+// every body, so the same bits.  Returns the first tail colour (ncolors: no tail).
+__device__ __forceinline__ unsigned int tail_start(const unsigned int *s_off, unsigned int ncolors, unsigned int limit) {
+    unsigned int acc = 0u, nonempty = 0u, t = ncolors;
+    for (unsigned int c = ncolors; c-- > 1u;) {
+        const unsigned int sz = s_off[c + 1] - s_off[c];
+        if (acc + sz > limit) break;
+        acc += sz;
+        t = c;
+        if (sz) ++nonempty;
+    }
+    return nonempty >= 2u ? t : ncolors;
 }
 
 // `phases`: bit 0 = colouring + ordering + solver records + warm start, bit 1 = `iterations` sweeps,
@@ -409,9 +430,19 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
         return;
     }
     // ---- phase 3: solver records + warm start, one colour at a time
-    for (unsigned int c = 0; c < s_ncolors; ++c) {
+    const unsigned int tail3 = tail_start(s_off, s_ncolors, (unsigned int) w.solve_tail);
+    for (unsigned int c = 0; c < tail3; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
         for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, gvel, inv_dt);
+        grid.sync();
+    }
+    if (tail3 < s_ncolors) {
+        if (blockIdx.x == 0)
+            for (unsigned int c = tail3; c < s_ncolors; ++c) {
+                if (s_off[c] == s_off[c + 1]) continue;
+                for (unsigned int s = s_off[c] + threadIdx.x; s < s_off[c + 1]; s += blockDim.x) prepare_and_warm_start(w, man, w.order[s], s, gvel, inv_dt);
+                __syncthreads();
+            }
         grid.sync();
     }
     } else {
@@ -425,13 +456,24 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     // ---- phase 4: Gauss-Seidel sweeps
     // ([measured] fetching the next colour's records BEFORE the barrier -- software pipelining across grid.sync() --
     // was bit-identical and slower: solve 0.313 -> 0.432 ms at 65k bodies; the barrier's fence waits for the loads)
+    const unsigned int tail4 = tail_start(s_off, ncolors, (unsigned int) w.solve_tail);
     if (phases & SV_SWEEP)
-    for (int it = 0; it < iterations; ++it)
-        for (unsigned int c = 0; c < ncolors; ++c) {
+    for (int it = 0; it < iterations; ++it) {
+        for (unsigned int c = 0; c < tail4; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
             for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one(w, s, gvel2);
             grid.sync();
         }
+        if (tail4 < ncolors) {
+            if (blockIdx.x == 0)
+                for (unsigned int c = tail4; c < ncolors; ++c) {
+                    if (s_off[c] == s_off[c + 1]) continue;
+                    for (unsigned int s = s_off[c] + threadIdx.x; s < s_off[c + 1]; s += blockDim.x) sweep_one(w, s, gvel2);
+                    __syncthreads();
+                }
+            grid.sync();
+        }
+    }
     // ---- phase 5: write the impulses and effective masses back to the cache
     if (phases & SV_WRITEBACK)
     for (unsigned int s = tid; s < M; s += nth) {

@@ -700,6 +700,7 @@ static void fill_dev_params(frWorld *w, float dt) {
         if (d.sort_launch > FX_SORT_MAX_PASSES) d.sort_launch = FX_SORT_MAX_PASSES;
     }
     { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }
+    { static const int tl = [] { const char *e = std::getenv("FEROX_SOLVE_TAIL"); return e ? std::atoi(e) : 2048; }(); d.solve_tail = tl; }
     {
         // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
         const bool contact_major = w->force_large || w->manifold_hint >= 400000;
@@ -1517,12 +1518,19 @@ struct HandlerBridge {
     ManifoldRec *dev = nullptr;
     unsigned int *idx = nullptr;         // reference-order mode: dense index per visited entry
     size_t cap = 0;
+    cudaStream_t up = nullptr;           // uploads of finished chunks run beside the downloads of later ones
+    cudaEvent_t up_done = nullptr;
+    std::vector<cudaEvent_t> landed;     // one per chunk: its download has completed
     ~HandlerBridge() {
         if (host) cudaFreeHost(host);
         cudaFree(dev);
         cudaFree(idx);
+        for (cudaEvent_t e : landed) cudaEventDestroy(e);
+        if (up_done) cudaEventDestroy(up_done);
+        if (up) cudaStreamDestroy(up);
     }
 };
+#define FX_BRIDGE_CHUNK 32768u          // records per pipelined chunk (3.2 MB)
 static bool bridge_reserve(HandlerBridge &hb, size_t n) {
     if (n <= hb.cap) return true;
     if (hb.host) cudaFreeHost(hb.host);
@@ -1547,22 +1555,42 @@ static void run_handler(frWorld *w, frCollisionEventFunc fn) {
     cudaMemcpyAsync(&n, serial ? w->so.r_len : &d.ctr->n_manifolds, sizeof(unsigned int), cudaMemcpyDeviceToHost, s);
     if (!fx_cuda_ok(cudaStreamSynchronize(s), "manifold count") || n == 0 || d.cap_manifolds == 0) return;
     if (!bridge_reserve(hb, n)) return;
+    fx_world_pull(w);   // getters inside the handler must see current state (before the chunk copies queue up behind it)
+    if (!hb.up) {
+        cudaStreamCreateWithFlags(&hb.up, cudaStreamNonBlocking);
+        cudaEventCreateWithFlags(&hb.up_done, cudaEventDisableTiming);
+    }
+    const unsigned int nchunks = (n + FX_BRIDGE_CHUNK - 1u) / FX_BRIDGE_CHUNK;
+    while (hb.landed.size() < nchunks) {
+        cudaEvent_t e;
+        cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+        hb.landed.push_back(e);
+    }
     if (serial) fx_launch_visit_index(d, w->cx, w->so, hb.idx, n);
     fx_launch_pack_collisions(d, w->cx, serial ? hb.idx : nullptr, n, hb.dev);
-    cudaMemcpyAsync(hb.host, hb.dev, (size_t) n * sizeof(frxManifold), cudaMemcpyDeviceToHost, s);
-    if (!fx_cuda_ok(cudaStreamSynchronize(s), "manifold download")) return;
-    fx_world_pull(w);   // getters inside the handler must see current state
+    // pipeline: chunk k is handed to the callbacks while chunk k+1.. still download and chunk k-1 uploads
+    for (unsigned int k = 0; k < nchunks; ++k) {
+        const size_t lo = (size_t) k * FX_BRIDGE_CHUNK, cnt = (k + 1u == nchunks) ? n - lo : FX_BRIDGE_CHUNK;
+        cudaMemcpyAsync(hb.host + lo, hb.dev + lo, cnt * sizeof(frxManifold), cudaMemcpyDeviceToHost, s);
+        cudaEventRecord(hb.landed[k], s);
+    }
     const int nb = (int) w->bodies.size();
     frBody *const *bodies = w->bodies.data();
-    for (unsigned int i = 0; i < n; ++i) {
-        frxManifold &rec = hb.host[i];
-        if (rec.value.count <= 0) continue;
-        frBodyPair pair;
-        pair.first = (rec.first >= 0 && rec.first < nb) ? bodies[rec.first] : nullptr;
-        pair.second = (rec.second >= 0 && rec.second < nb) ? bodies[rec.second] : nullptr;
-        fn(pair, &rec.value);
+    for (unsigned int k = 0; k < nchunks; ++k) {
+        const size_t lo = (size_t) k * FX_BRIDGE_CHUNK, cnt = (k + 1u == nchunks) ? n - lo : FX_BRIDGE_CHUNK;
+        if (!fx_cuda_ok(cudaEventSynchronize(hb.landed[k]), "manifold download")) return;
+        for (size_t i = lo; i < lo + cnt; ++i) {
+            frxManifold &rec = hb.host[i];
+            if (rec.value.count <= 0) continue;
+            frBodyPair pair;
+            pair.first = (rec.first >= 0 && rec.first < nb) ? bodies[rec.first] : nullptr;
+            pair.second = (rec.second >= 0 && rec.second < nb) ? bodies[rec.second] : nullptr;
+            fn(pair, &rec.value);
+        }
+        cudaMemcpyAsync(hb.dev + lo, hb.host + lo, cnt * sizeof(frxManifold), cudaMemcpyHostToDevice, hb.up);
     }
-    cudaMemcpyAsync(hb.dev, hb.host, (size_t) n * sizeof(frxManifold), cudaMemcpyHostToDevice, s);
+    cudaEventRecord(hb.up_done, hb.up);
+    cudaStreamWaitEvent(s, hb.up_done, 0);
     fx_launch_unpack_collisions(d, w->cx, serial ? hb.idx : nullptr, n, hb.dev);
 }
 void fx_release_bridge(frWorld *w) {
