@@ -80,7 +80,7 @@ void fx_launch_rehash_prev(const DevWorld &w, const FxLaunchCtx &cx);
 void fx_launch_serial_reindex(const FxLaunchCtx &cx, const SerialOrder &o);
 // collision-handler bridge: live manifolds <-> packed public records, in visiting order (idx: reference-order mode)
 void fx_launch_visit_index(const DevWorld &w, const FxLaunchCtx &cx, const SerialOrder &o, unsigned int *idx, unsigned int cap);
-void fx_launch_pack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, ManifoldRec *out);
+void fx_launch_pack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, ManifoldRec *out, int4 *head);
 void fx_launch_unpack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, const ManifoldRec *in);
 
 // world ray casts on the device state (fx_bodies.cu): rays = frRay[nrays], hits = frRaycastHit[nrays][max_hits] with the world

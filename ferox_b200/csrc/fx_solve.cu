@@ -239,23 +239,6 @@ __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, con
     sweep_apply(w, s, q, vel.load(q.b.x), vel.load(q.b.y), vel);
 }
 
-// Tail colours.  A settled pile needs as many colours as its busiest body has contacts, but the last ones hold a
-// handful of manifolds ([measured] config 2: 25371, 23942, 22512, 20101, 16451, 10719, 1263, 33) while every colour
-// costs a grid barrier in every sweep.  The trailing colours that together hold at most `limit` manifolds are
-// therefore swept by block 0 alone, one after the other with block barriers, behind ONE grid barrier: same order on
-// every body, so the same bits.  Returns the first tail colour (ncolors: no tail).
-__device__ __forceinline__ unsigned int tail_start(const unsigned int *s_off, unsigned int ncolors, unsigned int limit) {
-    unsigned int acc = 0u, nonempty = 0u, t = ncolors;
-    for (unsigned int c = ncolors; c-- > 1u;) {
-        const unsigned int sz = s_off[c + 1] - s_off[c];
-        if (acc + sz > limit) break;
-        acc += sz;
-        t = c;
-        if (sz) ++nonempty;
-    }
-    return nonempty >= 2u ? t : ncolors;
-}
-
 // `phases`: bit 0 = colouring + ordering + solver records + warm start, bit 1 = `iterations` sweeps,
 // bit 2 = write-back.  A plain step launches all three at once; a strip-decomposed world launches
 // them separately so that ghost velocities can be refreshed between sweeps.
@@ -430,19 +413,9 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
         return;
     }
     // ---- phase 3: solver records + warm start, one colour at a time
-    const unsigned int tail3 = tail_start(s_off, s_ncolors, (unsigned int) w.solve_tail);
-    for (unsigned int c = 0; c < tail3; ++c) {
+    for (unsigned int c = 0; c < s_ncolors; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
         for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, gvel, inv_dt);
-        grid.sync();
-    }
-    if (tail3 < s_ncolors) {
-        if (blockIdx.x == 0)
-            for (unsigned int c = tail3; c < s_ncolors; ++c) {
-                if (s_off[c] == s_off[c + 1]) continue;
-                for (unsigned int s = s_off[c] + threadIdx.x; s < s_off[c + 1]; s += blockDim.x) prepare_and_warm_start(w, man, w.order[s], s, gvel, inv_dt);
-                __syncthreads();
-            }
         grid.sync();
     }
     } else {
@@ -456,24 +429,16 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     // ---- phase 4: Gauss-Seidel sweeps
     // ([measured] fetching the next colour's records BEFORE the barrier -- software pipelining across grid.sync() --
     // was bit-identical and slower: solve 0.313 -> 0.432 ms at 65k bodies; the barrier's fence waits for the loads)
-    const unsigned int tail4 = tail_start(s_off, ncolors, (unsigned int) w.solve_tail);
+    // ([measured] sweeping the sparse trailing colours -- config 2: 25371, 23942, 22512, 20101, 16451, 10719, 1263, 33 manifolds
+    // per colour -- by block 0 alone behind ONE grid barrier was bit-identical and slower, solve 0.296 -> 0.343 ms: three
+    // block-serial rounds of dependent L2 round trips cost more than the barrier they save)
     if (phases & SV_SWEEP)
-    for (int it = 0; it < iterations; ++it) {
-        for (unsigned int c = 0; c < tail4; ++c) {
+    for (int it = 0; it < iterations; ++it)
+        for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
             for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one(w, s, gvel2);
             grid.sync();
         }
-        if (tail4 < ncolors) {
-            if (blockIdx.x == 0)
-                for (unsigned int c = tail4; c < ncolors; ++c) {
-                    if (s_off[c] == s_off[c + 1]) continue;
-                    for (unsigned int s = s_off[c] + threadIdx.x; s < s_off[c + 1]; s += blockDim.x) sweep_one(w, s, gvel2);
-                    __syncthreads();
-                }
-            grid.sync();
-        }
-    }
     // ---- phase 5: write the impulses and effective masses back to the cache
     if (phases & SV_WRITEBACK)
     for (unsigned int s = tid; s < M; s += nth) {
@@ -525,7 +490,7 @@ __global__ void k_group_scatter(DevWorld w) {
     }
 }
 
-__global__ void k_solve_local(DevWorld w, int iterations, int max_bodies) {
+__global__ void __launch_bounds__(1024, 1) k_solve_local(DevWorld w, int iterations, int max_bodies) {
     extern __shared__ __align__(16) unsigned char lsm[];
     float4 *svel = reinterpret_cast<float4 *>(lsm);
     unsigned long long *smask = reinterpret_cast<unsigned long long *>(lsm + (size_t) max_bodies * 16);
@@ -862,7 +827,9 @@ __global__ void __launch_bounds__(MB_BLOCK) k_visit_index(DevWorld w, SerialOrde
     }
 }
 
-__global__ void __launch_bounds__(MB_BLOCK) k_pack_collisions(DevWorld w, const unsigned int *idx, unsigned int n, ManifoldRec *out) {
+// `head`: {first, second, count, 0} per record -- all the host's callback loop itself needs to read (16 B instead of two
+// cache lines of the 100-byte record, which only a callback that looks at its manifold touches)
+__global__ void __launch_bounds__(MB_BLOCK) k_pack_collisions(DevWorld w, const unsigned int *idx, unsigned int n, ManifoldRec *out, int4 *head) {
     __shared__ unsigned int s_rec[MB_BLOCK * MB_WORDS];       // odd record stride: conflict-free per-thread fills
     const ManifoldSet man = w.man[*w.cur_flip];
     for (unsigned int base = blockIdx.x * MB_BLOCK; base < n; base += gridDim.x * MB_BLOCK) {
@@ -886,6 +853,7 @@ __global__ void __launch_bounds__(MB_BLOCK) k_pack_collisions(DevWorld w, const 
                 ct.normalMass = im.x; ct.normalScalar = im.y; ct.tangentMass = im.z; ct.tangentScalar = im.w;
             }
         }
+        if (r < n) head[r] = make_int4(rec.first, rec.second, rec.value.count, 0);
         const unsigned int *src = reinterpret_cast<const unsigned int *>(&rec);
 #pragma unroll
         for (int k = 0; k < MB_WORDS; ++k) s_rec[threadIdx.x * MB_WORDS + k] = src[k];
@@ -931,10 +899,10 @@ void fx_launch_visit_index(const DevWorld &w, const FxLaunchCtx &cx, const Seria
     long long g = ((long long) cap + MB_BLOCK - 1) / MB_BLOCK;
     k_visit_index<<<(int) (g < 1 ? 1 : (g > cx.max_blocks ? cx.max_blocks : g)), MB_BLOCK, 0, cx.stream>>>(w, o, idx); ++g_fx_launches;
 }
-void fx_launch_pack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, ManifoldRec *out) {
+void fx_launch_pack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, ManifoldRec *out, int4 *head) {
     if (n == 0) return;
     long long g = ((long long) n + MB_BLOCK - 1) / MB_BLOCK;
-    k_pack_collisions<<<(int) (g > cx.max_blocks ? cx.max_blocks : g), MB_BLOCK, 0, cx.stream>>>(w, idx, n, out); ++g_fx_launches;
+    k_pack_collisions<<<(int) (g > cx.max_blocks ? cx.max_blocks : g), MB_BLOCK, 0, cx.stream>>>(w, idx, n, out, head); ++g_fx_launches;
 }
 void fx_launch_unpack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *idx, unsigned int n, const ManifoldRec *in) {
     if (n == 0) return;

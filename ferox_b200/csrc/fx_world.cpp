@@ -700,7 +700,6 @@ static void fill_dev_params(frWorld *w, float dt) {
         if (d.sort_launch > FX_SORT_MAX_PASSES) d.sort_launch = FX_SORT_MAX_PASSES;
     }
     { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }
-    { static const int tl = [] { const char *e = std::getenv("FEROX_SOLVE_TAIL"); return e ? std::atoi(e) : 2048; }(); d.solve_tail = tl; }
     {
         // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
         const bool contact_major = w->force_large || w->manifold_hint >= 400000;
@@ -1516,6 +1515,7 @@ static void visiting_order(const ManifoldHost &mh, std::vector<unsigned int> &or
 struct HandlerBridge {
     frxManifold *host = nullptr;         // pinned
     ManifoldRec *dev = nullptr;
+    int4 *head_host = nullptr, *head_dev = nullptr;   // {first, second, count, 0}: what the callback loop itself reads
     unsigned int *idx = nullptr;         // reference-order mode: dense index per visited entry
     size_t cap = 0;
     cudaStream_t up = nullptr;           // uploads of finished chunks run beside the downloads of later ones
@@ -1523,7 +1523,9 @@ struct HandlerBridge {
     std::vector<cudaEvent_t> landed;     // one per chunk: its download has completed
     ~HandlerBridge() {
         if (host) cudaFreeHost(host);
+        if (head_host) cudaFreeHost(head_host);
         cudaFree(dev);
+        cudaFree(head_dev);
         cudaFree(idx);
         for (cudaEvent_t e : landed) cudaEventDestroy(e);
         if (up_done) cudaEventDestroy(up_done);
@@ -1534,12 +1536,16 @@ struct HandlerBridge {
 static bool bridge_reserve(HandlerBridge &hb, size_t n) {
     if (n <= hb.cap) return true;
     if (hb.host) cudaFreeHost(hb.host);
+    if (hb.head_host) cudaFreeHost(hb.head_host);
     cudaFree(hb.dev);
+    cudaFree(hb.head_dev);
     cudaFree(hb.idx);
-    hb.host = nullptr; hb.dev = nullptr; hb.idx = nullptr;
+    hb.host = nullptr; hb.dev = nullptr; hb.idx = nullptr; hb.head_host = nullptr; hb.head_dev = nullptr;
     hb.cap = n + n / 4 + 1024;
     const bool ok = fx_cuda_ok(cudaMallocHost((void **) &hb.host, hb.cap * sizeof(frxManifold)), "cudaMallocHost bridge") &&
+                    fx_cuda_ok(cudaMallocHost((void **) &hb.head_host, hb.cap * sizeof(int4)), "cudaMallocHost bridge") &&
                     fx_cuda_ok(cudaMalloc((void **) &hb.dev, hb.cap * sizeof(ManifoldRec)), "cudaMalloc bridge") &&
+                    fx_cuda_ok(cudaMalloc((void **) &hb.head_dev, hb.cap * sizeof(int4)), "cudaMalloc bridge") &&
                     fx_cuda_ok(cudaMalloc((void **) &hb.idx, hb.cap * sizeof(unsigned int)), "cudaMalloc bridge");
     if (!ok) hb.cap = 0;
     return ok;
@@ -1567,7 +1573,8 @@ static void run_handler(frWorld *w, frCollisionEventFunc fn) {
         hb.landed.push_back(e);
     }
     if (serial) fx_launch_visit_index(d, w->cx, w->so, hb.idx, n);
-    fx_launch_pack_collisions(d, w->cx, serial ? hb.idx : nullptr, n, hb.dev);
+    fx_launch_pack_collisions(d, w->cx, serial ? hb.idx : nullptr, n, hb.dev, hb.head_dev);
+    cudaMemcpyAsync(hb.head_host, hb.head_dev, (size_t) n * sizeof(int4), cudaMemcpyDeviceToHost, s);
     // pipeline: chunk k is handed to the callbacks while chunk k+1.. still download and chunk k-1 uploads
     for (unsigned int k = 0; k < nchunks; ++k) {
         const size_t lo = (size_t) k * FX_BRIDGE_CHUNK, cnt = (k + 1u == nchunks) ? n - lo : FX_BRIDGE_CHUNK;
@@ -1580,12 +1587,12 @@ static void run_handler(frWorld *w, frCollisionEventFunc fn) {
         const size_t lo = (size_t) k * FX_BRIDGE_CHUNK, cnt = (k + 1u == nchunks) ? n - lo : FX_BRIDGE_CHUNK;
         if (!fx_cuda_ok(cudaEventSynchronize(hb.landed[k]), "manifold download")) return;
         for (size_t i = lo; i < lo + cnt; ++i) {
-            frxManifold &rec = hb.host[i];
-            if (rec.value.count <= 0) continue;
+            const int4 h = hb.head_host[i];
+            if (h.z <= 0) continue;
             frBodyPair pair;
-            pair.first = (rec.first >= 0 && rec.first < nb) ? bodies[rec.first] : nullptr;
-            pair.second = (rec.second >= 0 && rec.second < nb) ? bodies[rec.second] : nullptr;
-            fn(pair, &rec.value);
+            pair.first = (h.x >= 0 && h.x < nb) ? bodies[h.x] : nullptr;
+            pair.second = (h.y >= 0 && h.y < nb) ? bodies[h.y] : nullptr;
+            fn(pair, &hb.host[i].value);
         }
         cudaMemcpyAsync(hb.dev + lo, hb.host + lo, cnt * sizeof(frxManifold), cudaMemcpyHostToDevice, hb.up);
     }
