@@ -52,6 +52,7 @@ EXT_PROTOTYPES = {
     "frxStripGetNcclUniqueId": (I, [P]),
     "frxStripInitNccl": (I, [P, I, I, P]),
     "frxStripStep": (None, [C.POINTER(C.c_void_p), I, F]),
+    "frxStripMigrate": (I, [C.POINTER(C.c_void_p), I]),
     "frxSetWorldSolverMode": (None, [P, I]),
     "frxGetWorldSolverMode": (I, [P]),
     "frxSetWorldTimestamp": (None, [P, F]),

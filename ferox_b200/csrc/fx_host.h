@@ -164,6 +164,10 @@ struct frWorld_ {
         cudaEvent_t sent = nullptr;                  // my copies into the neighbours' receive buffers are done
         cudaEvent_t consumed = nullptr;              // I have read my receive buffers (neighbours may overwrite them)
         bool ghosts_primed = false;
+        // ownership migration (frxStripMigrate): rows that change rank travel through these (NCCL neighbours only)
+        unsigned char *mig_send[2] = { nullptr, nullptr }, *mig_recv[2] = { nullptr, nullptr };      // device, [left, right]
+        unsigned char *mig_hsend[2] = { nullptr, nullptr }, *mig_hrecv[2] = { nullptr, nullptr };    // pinned host
+        long long migrated_out = 0, migrated_in = 0;
     } strip;
 
     // CUDA graph of the fixed launch sequence of a step (production mode, no handler, no profiling).

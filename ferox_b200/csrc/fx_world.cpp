@@ -148,6 +148,7 @@ extern "C" frWorld *frCreateWorld(frVector2 gravity, float cellSize) {
     return w;
 }
 
+void fx_strip_release_comm(frWorld *w);
 static void free_manifold_set(ManifoldSet &m) {
     cudaFree(m.key); cudaFree(m.body); cudaFree(m.hdr); cudaFree(m.meta); cudaFree(m.geo); cudaFree(m.imp); cudaFree(m.cid);
     std::memset(&m, 0, sizeof m);
@@ -174,6 +175,12 @@ static void world_free_device(frWorld *w) {
     cudaFree(w->strip.send_delta); cudaFree(w->strip.recv_delta); cudaFree(w->strip.ghost_before); cudaFree(w->strip.border_before);
     cudaFree(w->strip.ghost_split); cudaFree(w->strip.border_split);
     cudaFree(w->strip.border_idx); cudaFree(w->strip.ghost_cnt);
+    for (int side = 0; side < 2; ++side) {
+        cudaFree(w->strip.mig_send[side]); cudaFree(w->strip.mig_recv[side]);
+        if (w->strip.mig_hsend[side]) cudaFreeHost(w->strip.mig_hsend[side]);
+        if (w->strip.mig_hrecv[side]) cudaFreeHost(w->strip.mig_hrecv[side]);
+    }
+    fx_strip_release_comm(w);
     if (w->strip.sent) cudaEventDestroy(w->strip.sent);
     if (w->strip.consumed) cudaEventDestroy(w->strip.consumed);
     cudaFree(w->d_snapshot);
@@ -197,6 +204,9 @@ static void world_free_device(frWorld *w) {
 }
 
 static void detach_body(frWorld *w, frBody *b);
+static void attach_body(frWorld *w, frBody *b);
+void fx_strip_release_comm(frWorld *w);
+static void fx_strip_abort_comm(frWorld *w);
 
 void fx_release_manifold_host(frWorld *w);
 void fx_release_bridge(frWorld *w);
@@ -1103,6 +1113,7 @@ struct NcclApi {
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void *) = nullptr;
+    int (*CommAbort)(void *) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -1119,6 +1130,7 @@ bool nccl_load() {
     *(void **) &g_nccl.GroupStart = dlsym(h, "ncclGroupStart");
     *(void **) &g_nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
     *(void **) &g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
+    *(void **) &g_nccl.CommAbort = dlsym(h, "ncclCommAbort");
     *(void **) &g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
     return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
 }
@@ -1202,6 +1214,16 @@ extern "C" int frxStripLinkLocal(frWorld *left, frWorld *right) {
         }
     }
     return 0;
+}
+
+void fx_strip_release_comm(frWorld *w) {
+    if (w->strip.nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(w->strip.nccl_comm);
+    w->strip.nccl_comm = nullptr;
+}
+static void fx_strip_abort_comm(frWorld *w) {
+    if (w->strip.nccl_comm && g_nccl.CommAbort) g_nccl.CommAbort(w->strip.nccl_comm);
+    w->strip.nccl_comm = nullptr;
+    fx_set_error(7, "strip step failed after its first exchange: the NCCL communicator was aborted");
 }
 
 extern "C" int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *uniqueId128) {
@@ -1295,6 +1317,7 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
             fx_launch_strip_unpack(w->dw, w->cx, st.recv_full, w->dw.n_owned, st.ghost_cap, st.ghost_cnt);
             st.ghosts_primed = true;
         }
+        // (nothing has been exchanged yet: a failure here leaves no neighbour waiting inside a send/recv group)
         if (w->cx.zero_base == nullptr && !ensure_work_capacity(w, 8ull * rows + 4096, 16ull * rows + 4096, 4ull * rows + 4096)) return;
         fill_dev_params(w, dt);
         const bool has_left = st.peer[0] != nullptr || (st.nccl_comm && st.rank > 0);
@@ -1313,7 +1336,12 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
         fx_launch_strip_unpack(d, w->cx, st.recv_full, d.n_owned, st.ghost_cap, st.ghost_cnt);
         cudaEventRecord(st.consumed, w->stream);
         if (w->needs_sizing) {
-            if (!sizing_prepass(w, dt)) return;
+            if (!sizing_prepass(w, dt)) {
+                // the neighbours are already inside this step's exchanges: tear the communicator down so that they
+                // fail loudly instead of waiting for a message that will never come
+                fx_strip_abort_comm(w);
+                return;
+            }
             w->needs_sizing = false;
         } else {
             grow_if_crowded(w);
@@ -1377,6 +1405,166 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
         fx_cuda_ok(cudaGetLastError(), "strip step launch");
         if (w->ring_head != w->ring_tail) drain_queue(w);
     }
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// ownership migration between strips
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct MigRow {                         // one body on its way to another rank (112 B)
+    float4 posrot, vel, force, aabb;
+    float angle, gravity_scale;
+    int type, shape_idx;
+    unsigned int flags, pad[7];
+};
+static_assert(sizeof(MigRow) == 112, "MigRow layout");
+size_t mig_bytes(const frWorld *w) { return FX_MSG_HEADER + (size_t) w->strip.ghost_cap * sizeof(MigRow); }
+
+bool mig_reserve(frWorld *w) {
+    frWorld_::Strip &st = w->strip;
+    if (st.mig_send[0]) return true;
+    bool ok = true;
+    for (int side = 0; side < 2 && ok; ++side)
+        ok = fx_cuda_ok(cudaMalloc((void **) &st.mig_send[side], mig_bytes(w)), "cudaMalloc migrate") &&
+             fx_cuda_ok(cudaMalloc((void **) &st.mig_recv[side], mig_bytes(w)), "cudaMalloc migrate") &&
+             fx_cuda_ok(cudaMallocHost((void **) &st.mig_hsend[side], mig_bytes(w)), "cudaMallocHost migrate") &&
+             fx_cuda_ok(cudaMallocHost((void **) &st.mig_hrecv[side], mig_bytes(w)), "cudaMallocHost migrate");
+    return ok;
+}
+}   // namespace
+
+extern "C" int frxStripMigrate(frWorld **ws, int n) {
+    if (!ws || n <= 0) return -1;
+    for (int k = 0; k < n; ++k)
+        if (!ws[k] || !ws[k]->strip.enabled || !ws[k]->device_ok) { fx_set_error(5, "frxStripMigrate: world is not a configured strip"); return -1; }
+    long long moved = 0;
+    // ---- who leaves: positions on the host, emigrants per side
+    std::vector<std::vector<frBody *>> out_left((size_t) n), out_right((size_t) n);
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        cudaSetDevice(w->device);
+        fx_world_pull(w);
+        const frWorld_::Strip &st = w->strip;
+        const float h = 0.25f * st.margin;
+        const bool has_left = st.peer[0] != nullptr || (st.nccl_comm && st.rank > 0);
+        const bool has_right = st.peer[1] != nullptr || (st.nccl_comm && st.rank + 1 < st.nranks);
+        for (size_t i = 0; i < w->bodies.size(); ++i) {
+            frBody *b = w->bodies[i];
+            if (b->type == FR_BODY_STATIC) continue;           // static bodies are replicated, never exchanged
+            const float px = w->h.posrot[i].x;
+            if (has_left && px < st.cut_lo - h) out_left[(size_t) k].push_back(b);
+            else if (has_right && px >= st.cut_hi + h) out_right[(size_t) k].push_back(b);
+        }
+    }
+    // ---- in-process neighbours: the body itself changes world
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        for (int side = 0; side < 2; ++side) {
+            frWorld *p = w->strip.peer[side];
+            if (!p) continue;
+            std::vector<frBody *> &list = side == 0 ? out_left[(size_t) k] : out_right[(size_t) k];
+            for (frBody *b : list) {
+                if ((int) p->bodies.size() >= p->capacity) break;
+                // every strip registered the same shape list in the same order (frxStripRegisterShapes): the body takes
+                // the neighbour's copy of its shape, so that shape-table indices keep meaning the same thing everywhere
+                auto it = w->shape_index.find(b->shape);
+                if (b->shape != nullptr && (it == w->shape_index.end() || it->second >= (int) p->shape_list.size())) continue;
+                cudaSetDevice(w->device);
+                detach_body(w, b);
+                if (b->shape != nullptr) b->shape = p->shape_list[(size_t) it->second];
+                cudaSetDevice(p->device);
+                attach_body(p, b);
+                // (attach_body clears the accumulators as a queue drain would; a migrant keeps what it carried)
+                p->h.force[b->index] = b->loc.force;
+                ++moved;
+                ++w->strip.migrated_out;
+                ++p->strip.migrated_in;
+            }
+            list.clear();
+        }
+    }
+    // ---- NCCL neighbours: rows travel, bodies are re-created on arrival
+    for (int k = 0; k < n; ++k) {
+        frWorld *w = ws[k];
+        frWorld_::Strip &st = w->strip;
+        if (!st.nccl_comm) continue;
+        cudaSetDevice(w->device);
+        if (!mig_reserve(w)) return -1;
+        cudaStream_t s = w->stream;
+        const int left = st.rank - 1, right = st.rank + 1;
+        std::vector<frBody *> sent[2];
+        for (int side = 0; side < 2; ++side) {
+            std::vector<frBody *> &list = side == 0 ? out_left[(size_t) k] : out_right[(size_t) k];
+            unsigned int cnt = 0;
+            MigRow *rows = reinterpret_cast<MigRow *>(st.mig_hsend[side] + FX_MSG_HEADER);
+            for (frBody *b : list) {
+                if (cnt >= st.ghost_cap) break;                 // the rest goes with the next call
+                const int i = b->index;
+                MigRow r;
+                std::memset(&r, 0, sizeof r);
+                r.posrot = w->h.posrot[i]; r.vel = w->h.vel[i]; r.force = w->h.force[i]; r.aabb = w->h.aabb[i];
+                r.angle = w->h.angle[i];
+                r.gravity_scale = b->gravity_scale;
+                r.type = (int) b->type;
+                r.flags = (unsigned int) b->flags;
+                r.shape_idx = w->h.shape[i].x;
+                rows[cnt++] = r;
+                sent[side].push_back(b);
+            }
+            std::memset(st.mig_hsend[side], 0, FX_MSG_HEADER);
+            *reinterpret_cast<unsigned int *>(st.mig_hsend[side]) = cnt;
+            cudaMemcpyAsync(st.mig_send[side], st.mig_hsend[side], FX_MSG_HEADER + (size_t) cnt * sizeof(MigRow), cudaMemcpyHostToDevice, s);
+        }
+        g_nccl.GroupStart();
+        if (left >= 0) {
+            g_nccl.Send(st.mig_send[0], mig_bytes(w), 0, left, st.nccl_comm, s);
+            g_nccl.Recv(st.mig_recv[0], mig_bytes(w), 0, left, st.nccl_comm, s);
+        }
+        if (right < st.nranks) {
+            g_nccl.Send(st.mig_send[1], mig_bytes(w), 0, right, st.nccl_comm, s);
+            g_nccl.Recv(st.mig_recv[1], mig_bytes(w), 0, right, st.nccl_comm, s);
+        }
+        if (!nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd (migrate)")) return -1;
+        for (int side = 0; side < 2; ++side)
+            if ((side == 0 && left >= 0) || (side == 1 && right < st.nranks))
+                cudaMemcpyAsync(st.mig_hrecv[side], st.mig_recv[side], mig_bytes(w), cudaMemcpyDeviceToHost, s);
+        if (!fx_cuda_ok(cudaStreamSynchronize(s), "strip migration exchange")) return -1;
+        // the emigrants leave (their handles are released: the body now lives on another rank) ...
+        for (int side = 0; side < 2; ++side)
+            for (frBody *b : sent[side]) {
+                detach_body(w, b);
+                std::free(b);
+                ++moved;
+                ++st.migrated_out;
+            }
+        // ... and the immigrants arrive
+        for (int side = 0; side < 2; ++side) {
+            if (!((side == 0 && left >= 0) || (side == 1 && right < st.nranks))) continue;
+            unsigned int cnt = *reinterpret_cast<const unsigned int *>(st.mig_hrecv[side]);
+            if (cnt > st.ghost_cap) cnt = st.ghost_cap;
+            const MigRow *rows = reinterpret_cast<const MigRow *>(st.mig_hrecv[side] + FX_MSG_HEADER);
+            for (unsigned int r = 0; r < cnt; ++r) {
+                const MigRow &m = rows[r];
+                frShape *shape = (m.shape_idx >= 0 && m.shape_idx < (int) w->shape_list.size()) ? w->shape_list[(size_t) m.shape_idx] : nullptr;
+                frVector2 pos = { m.posrot.x, m.posrot.y };
+                frBody *b = frCreateBodyFromShape((frBodyType) m.type, pos, shape);
+                if (!b) continue;
+                if (m.flags) frSetBodyFlags(b, (frBodyFlags) m.flags);
+                if (m.gravity_scale != 1.0f) frSetBodyGravityScale(b, m.gravity_scale);
+                b->loc.posrot = m.posrot;
+                b->loc.angle = m.angle;
+                b->loc.vel = make_float4(m.vel.x, m.vel.y, m.vel.z, b->inv_mass);
+                b->loc.aabb = m.aabb;
+                b->loc.force = m.force;
+                if ((int) w->bodies.size() >= w->capacity) { std::free(b); continue; }
+                attach_body(w, b);
+                w->h.force[b->index] = m.force;
+                ++st.migrated_in;
+            }
+        }
+    }
+    return (int) moved;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -310,6 +310,15 @@ int frxStripLinkLocal(frWorld *left, frWorld *right);
 int frxStripGetNcclUniqueId(void *out128);
 int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *uniqueId128);
 void frxStripStep(frWorld **worlds, int nLocal, float dt);
+/* Ownership migration.  Every non-static body whose position has left its strip's x-interval by more than a quarter of
+   the margin changes owner: it is removed from its strip and added to the neighbour on that side, with its state
+   (transform, velocities, accumulated forces) intact; its contacts are found again by the new owner's next step (their
+   warm-start impulses start from zero once).  Collective: every process calls it at the same step with its strips in
+   the order it gives frxStripStep; call it every few dozen steps (it synchronises the strips and re-sizes their buffers).
+   In-process neighbours hand over the frBody itself.  Across processes (NCCL) the body is RE-CREATED on the receiving
+   rank -- reach it through frGetBodyInWorld -- and its handle on the sending rank is released: do not use it again.
+   Returns the number of bodies that left strips of this process, -1 on error. */
+int frxStripMigrate(frWorld **worlds, int nLocal);
 
 /* Introspection for parity tests: the candidate pairs (world indices, first < second, plus hit flag)
    of the last step, and the contact cache as (first index, second index, frCollision) records in

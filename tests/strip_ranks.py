@@ -27,6 +27,8 @@ def main():
     ap.add_argument("--steps", type=int, default=600)
     ap.add_argument("--margin", type=float, default=5.0)
     ap.add_argument("--ghost-cap", type=int, default=1024)
+    ap.add_argument("--migrate", type=int, default=0, help="frxStripMigrate every this many steps (0: static ownership)")
+    ap.add_argument("--push", type=float, default=0.0, help="initial x velocity of every dynamic body")
     args = ap.parse_args()
 
     import torch
@@ -52,6 +54,8 @@ def main():
     uid_bytes = bytes(uid.cpu().numpy().tobytes())
 
     spec = scenes.mixed_pile(args.bodies, width=args.width)
+    if args.push:
+        spec.vel[spec.body_type != capi.BODY_STATIC, 0] = args.push
     cuts = [args.width * (k + 1) / world for k in range(world - 1)]
     ss = scenes.StripScene(L, spec, cuts=cuts, margin=args.margin, ghost_cap=args.ghost_cap, rank=rank, devices={rank: local})
     assert L.frxStripInitNccl(ss.worlds[0], rank, world, uid_bytes) == 0, L.frxGetLastErrorString()
@@ -59,21 +63,29 @@ def main():
     L.frxSynchronizeWorld(ss.worlds[0])
     dist.barrier()
     t0 = time.perf_counter()
-    ss.step(args.steps)
+    moved = 0
+    if args.migrate > 0:
+        for _ in range(args.steps // args.migrate):
+            ss.step(args.migrate)
+            m = L.frxStripMigrate(ss._arr, 1)
+            assert m >= 0, L.frxGetLastErrorString()
+            moved += m
+    else:
+        ss.step(args.steps)
     L.frxSynchronizeWorld(ss.worlds[0])
     dist.barrier()
     ms = (time.perf_counter() - t0) * 1e3 / max(args.steps, 1)
     fb.check_error(L)
-    got = ss.gather_states()
+    # whatever this rank owns NOW (ownership may have migrated): every body that can move
+    views = fb.body_state_views(L, ss.worlds[0])
     ctr = fb.step_counters(L, ss.worlds[0])
     dyn = spec.body_type != capi.BODY_STATIC
-    mine = np.zeros(spec.n, bool)
-    mine[ss.owned[rank]] = True
-    mine &= dyn
-    y = got["pos"][mine, 1].astype(np.float64)
-    v2 = (got["vel"][mine].astype(np.float64) ** 2).sum(1)
-    sums = torch.tensor([y.sum(), float(mine.sum()), v2.sum(), float(ctr["manifolds"]), float((ctr["overflow"] & ~128) != 0),
-                         float(np.isfinite(got["pos"][mine]).all())], dtype=torch.float64, device=dev)
+    movable = views["vel"][:, 3] > 0
+    y = views["posrot"][movable, 1].astype(np.float64)
+    v2 = (views["vel"][movable, :2].astype(np.float64) ** 2).sum(1)
+    stray = float((ctr["overflow"] & 128) != 0)
+    sums = torch.tensor([y.sum(), float(movable.sum()), v2.sum(), float(ctr["manifolds"]), float((ctr["overflow"] & ~128) != 0),
+                         float(np.isfinite(views["posrot"][movable]).all()), float(moved), stray], dtype=torch.float64, device=dev)
     ymax = torch.tensor([y.max() if len(y) else -1e30], dtype=torch.float64, device=dev)
     dist.all_reduce(sums)
     dist.all_reduce(ymax, op=dist.ReduceOp.MAX)
@@ -91,7 +103,7 @@ def main():
                           "max_y": float(ymax.item()), "ke": s[2] / s[1],
                           "ke_single": float((want["vel"][dyn].astype(np.float64) ** 2).sum(1).mean()),
                           "manifolds": int(s[3]), "manifolds_single": int(wc["manifolds"]), "overflow": int(s[4]),
-                          "finite": int(s[5]) == world}), flush=True)
+                          "finite": int(s[5]) == world, "migrated": int(s[6]), "stray_ranks": int(s[7])}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

@@ -110,6 +110,23 @@ def test_two_strips_on_two_gpus_over_nccl(gpu):
     assert r["manifolds_single"] * 0.97 < r["manifolds"] < r["manifolds_single"] * 1.25, r
 
 
+def test_migration_over_nccl_on_two_gpus(gpu):
+    """The same sloshing pile with one process per GPU: migrants travel as rows over the library's NCCL communicator and
+    are re-created on the receiving rank; every body stays owned by exactly one rank and none is left behind."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29543", os.path.join(root, "tests", "strip_ranks.py"), "--bodies", "3000", "--steps", "600", "--migrate", "20",
+           "--push", "8.0"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert r["finite"] and r["overflow"] == 0 and r["stray_ranks"] == 0 and r["bodies"] == r["dynamic"] and r["migrated"] > 20, r
+    assert r["max_y"] < 0.6 and r["ke"] < 4.0 * r["ke_single"] + 1.0, r
+
+
 def test_eight_strips_of_the_65k_pile_match_the_single_world_statistically(gpu):
     """'parity shown by running the same code path at 65 k bodies on 2-8
     strips vs 1 GPU'.  The BASELINE config-2 pile (65,536 mixed bodies, 1,160 units wide) cut into 8
@@ -172,4 +189,46 @@ def test_ghost_overflow_and_stray_bodies_are_reported(gpu):
     for w in ss.worlds:
         L.frxSynchronizeWorld(w)
     assert fb.step_counters(L, ss.worlds[0])["overflow"] & 128
+    ss.release()
+
+
+def test_migration_keeps_a_sloshing_pile_whole(gpu):
+    """frxStripMigrate: a pile that starts out moving sideways carries hundreds of bodies across both cuts.  With the
+    ownership re-assigned every 20 steps no body is ever left outside its strip + margin (bit 128 never fires), every
+    body is owned by exactly one strip at the end, and the pile ends where the undivided world puts it."""
+    L = gpu
+    spec = scenes.mixed_pile(3000, width=100.0)
+    dyn = spec.body_type != capi.BODY_STATIC
+    spec.vel[dyn, 0] = 8.0
+    ss = scenes.StripScene(L, spec, cuts=[100.0 / 3.0, 200.0 / 3.0], margin=5.0, ghost_cap=1024)
+    index_of = {h: i for (k, i), h in ss.bodies.items() if dyn[i]}
+    ss.step(1)
+    moved = 0
+    for block in range(30):
+        ss.step(20)
+        m = L.frxStripMigrate(ss._arr, len(ss.worlds))
+        assert m >= 0, L.frxGetLastErrorString()
+        moved += m
+    fb.check_error(L)
+    pos = np.full((spec.n, 2), np.nan, np.float32)
+    vel = np.full((spec.n, 2), np.nan, np.float32)
+    owners = np.zeros(spec.n, np.int32)
+    for w in ss.worlds:
+        st = fb.body_states(L, w)
+        for j in range(L.frGetBodyCountInWorld(w)):
+            i = index_of.get(L.frGetBodyInWorld(w, j))
+            if i is not None:
+                pos[i], vel[i] = st["pos"][j], st["vel"][j]
+                owners[i] += 1
+        c = fb.step_counters(L, w)
+        assert c["overflow"] == 0, c                 # neither a dropped ghost (32) nor a body left behind (128), ever
+    assert (owners[dyn] == 1).all() and moved > 50, (moved, np.bincount(owners[dyn]))
+    assert np.isfinite(pos[dyn]).all()
+    want, wc = undivided(L, spec, 600)
+    for axis in (0, 1):
+        a, b = pos[dyn, axis].astype(np.float64).mean(), want["pos"][dyn, axis].astype(np.float64).mean()
+        assert abs(a - b) < 0.02 * abs(b) + 0.25, (axis, a, b)
+    assert pos[dyn, 1].max() < 0.6                    # nothing fell through the floor
+    ke = lambda v: float((v.astype(np.float64) ** 2).sum(1).mean())
+    assert ke(vel[dyn]) < 4.0 * ke(want["vel"][dyn]) + 0.5
     ss.release()
