@@ -845,17 +845,30 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
 
     def c5_multi():
         sc, spec = build_config5_strip(L, 1048576, rank, world_size, local_rank, dist, args.margin, args.ghost_cap)
-        n = L.frGetBodyCountInWorld(sc.world)
-        sc.step(600)
+        every = 50                                   # ownership migration period (steps), inside the timed region as well
+        moved = 0
+
+        def run(k):
+            nonlocal moved
+            done = 0
+            while done < k:
+                chunk = min(every, k - done)
+                sc.step(chunk)
+                done += chunk
+                if chunk == every:
+                    moved += max(0, L.frxStripMigrate(sc._arr, 1))
+        run(600)
         L.frxSynchronizeWorld(sc.world)
         sc.step(3)
         L.frxSynchronizeWorld(sc.world)
+        L.frxClearLastError()
         barrier()
         L.frxRecordEvent(sc.world, 0)
-        sc.step(steps)
+        run(steps)
         L.frxRecordEvent(sc.world, 1)
         elapsed = reduce_max(float(L.frxEventElapsedMs(sc.world, 0, 1)))
         barrier()
+        n = L.frGetBodyCountInWorld(sc.world)
         ctr = fb.step_counters(L, sc.world)
         total = reduce_sum(n)
         over = reduce_max(float(ctr["overflow"]))
@@ -864,11 +877,13 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
         sc.release()
         return {"workload": "config5: ONE pile of %d x 1,048,576 mixed bodies on 8 storeys cut into %d vertical strips, one per GPU; ghost "
                             "rows (96 B) once per step and 16-byte velocity changes after each of the 11 solver stages exchanged between "
-                            "neighbours with the library's own NCCL communicator (ncclSend/ncclRecv); settled 600 steps; one event bracket "
+                            "neighbours with the library's own NCCL communicator (ncclSend/ncclRecv); ownership migration (frxStripMigrate) every 50 "
+                            "steps, also inside the timed region; settled 600 steps; one event bracket "
                             "around %d steps, MAX over ranks (per-step working set > 2 GB per GPU)" % (world_size, world_size, steps),
                 "n_gpus": world_size, "nccl_ranks": world_size, "bodies_total": int(total), "steps": steps, "ms_per_step": elapsed / steps,
                 "hz": 1e3 * steps / elapsed, "value": total * steps / (elapsed * 1e-3), "unit": UNIT, "counters_rank0": ctr,
-                "overflow_max_over_ranks": int(over), "error_rank0": err}
+                "overflow_max_over_ranks": int(over), "error_rank0": err, "migration_every_steps": every,
+                "migrated_bodies_all_ranks": int(reduce_sum(moved))}
     out["config5"] = guarded("config5", c5_multi)
     return out
 
