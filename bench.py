@@ -862,6 +862,7 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
         sc.step(3)
         L.frxSynchronizeWorld(sc.world)
         L.frxClearLastError()
+        L.frxResetStepCounters(sc.world)             # `overflow` below: the timed region only
         barrier()
         L.frxRecordEvent(sc.world, 0)
         run(steps)

@@ -60,6 +60,7 @@ EXT_PROTOTYPES = {
     "frxStepWorldN": (None, [P, F, I]),
     "frxSynchronizeWorld": (None, [P]),
     "frxGetStepCounters": (None, [P, C.POINTER(StepCounters)]),
+    "frxResetStepCounters": (None, [P]),
     "frxGetBodyStates": (I, [P, P, P, P, P, P, P]),
     "frxViewBodyStates": (I, [P, P, P, P, P]),
     "frxClearLastError": (None, []),

@@ -710,6 +710,7 @@ static void fill_dev_params(frWorld *w, float dt) {
         if (d.sort_launch > FX_SORT_MAX_PASSES) d.sort_launch = FX_SORT_MAX_PASSES;
     }
     { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }
+    { static const int pf = [] { const char *e = std::getenv("FEROX_SOLVE_PREFETCH"); return e ? std::atoi(e) : 1; }(); d.solve_prefetch = pf; }
     {
         // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
         const bool contact_major = w->force_large || w->manifold_hint >= 400000;
@@ -1076,6 +1077,11 @@ extern "C" void frxSynchronizeWorld(frWorld *w) {
     read_snapshot(w, true);
 }
 
+extern "C" void frxResetStepCounters(frWorld *w) {
+    if (!w) return;
+    frxSynchronizeWorld(w);
+    w->sticky_overflow = 0;
+}
 extern "C" void frxGetStepCounters(frWorld *w, frxStepCounters *out) {
     if (!w || !out) return;
     frxSynchronizeWorld(w);
@@ -1465,7 +1471,7 @@ extern "C" int frxStripMigrate(frWorld **ws, int n) {
             if (!p) continue;
             std::vector<frBody *> &list = side == 0 ? out_left[(size_t) k] : out_right[(size_t) k];
             for (frBody *b : list) {
-                if ((int) p->bodies.size() >= p->capacity) break;
+                if ((int) p->bodies.size() >= p->capacity) p->capacity = (int) p->bodies.size() + 1;   // a move inside one world, not an add
                 // every strip registered the same shape list in the same order (frxStripRegisterShapes): the body takes
                 // the neighbour's copy of its shape, so that shape-table indices keep meaning the same thing everywhere
                 auto it = w->shape_index.find(b->shape);
@@ -1557,7 +1563,7 @@ extern "C" int frxStripMigrate(frWorld **ws, int n) {
                 b->loc.vel = make_float4(m.vel.x, m.vel.y, m.vel.z, b->inv_mass);
                 b->loc.aabb = m.aabb;
                 b->loc.force = m.force;
-                if ((int) w->bodies.size() >= w->capacity) { std::free(b); continue; }
+                if ((int) w->bodies.size() >= w->capacity) w->capacity = (int) w->bodies.size() + 1;       // a move inside one world, not an add
                 attach_body(w, b);
                 w->h.force[b->index] = m.force;
                 ++st.migrated_in;

@@ -258,6 +258,8 @@ void frxStepWorldN(frWorld *w, float dt, int n);
 /* block until all device work of `w` has finished (getters do this implicitly) */
 void frxSynchronizeWorld(frWorld *w);
 void frxGetStepCounters(frWorld *w, frxStepCounters *out);
+/* `overflow` accumulates (bitwise or) over all steps since the world was created or this was last called */
+void frxResetStepCounters(frWorld *w);
 
 /* Batch access to the bodies of a world in world-index order; every array is optional (NULL).
    Layouts: position float[n][2], angle float[n], sincos float[n][2], velocity float[n][2],

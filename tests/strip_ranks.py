@@ -65,11 +65,13 @@ def main():
     t0 = time.perf_counter()
     moved = 0
     if args.migrate > 0:
-        for _ in range(args.steps // args.migrate):
+        for block in range(args.steps // args.migrate):
             ss.step(args.migrate)
             m = L.frxStripMigrate(ss._arr, 1)
             assert m >= 0, L.frxGetLastErrorString()
             moved += m
+            if (block + 1) * args.migrate == 200:
+                L.frxResetStepCounters(ss.worlds[0])     # the landing is over: from here on no body may be left behind
     else:
         ss.step(args.steps)
     L.frxSynchronizeWorld(ss.worlds[0])
