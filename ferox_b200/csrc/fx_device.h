@@ -137,7 +137,6 @@ struct DevWorld {
     const StepScalars *scal;   // gravity, world clock, dt (see above)
     int solver_mode;
     int sort_launch;     // radix-sort passes the host launches this step (k_plan refuses a world whose keys need more)
-    int solve_prefetch;  // small-world solver: fetch the next phase's record inside the split grid barrier (FEROX_SOLVE_PREFETCH=0: off)
     int color_squeeze;   // how many of last step's top colours are re-coloured every step (0: never)
     int narrow_mode;     // 0: one lane per pair (default), 1: 8 lanes per pair with shuffle arg-max over axes
     // bodies

@@ -433,36 +433,10 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     // ([measured] sweeping the sparse trailing colours -- config 2: 25371, 23942, 22512, 20101, 16451, 10719, 1263, 33 manifolds
     // per colour -- by block 0 alone behind ONE grid barrier was bit-identical and slower, solve 0.296 -> 0.343 ms: three
     // block-serial rounds of dependent L2 round trips cost more than the barrier they save)
-    if ((phases & SV_SWEEP) && MINB == 1 && w.solve_prefetch) {
-        // Small worlds: a phase is a chain of dependent latencies (barrier -> record fetch -> velocity gather -> ~160
-        // dependent instructions -> store drain).  The record of a thread's NEXT manifold does not depend on any velocity,
-        // so it is fetched between the two halves of a SPLIT grid barrier -- after this block has arrived, while the
-        // arrival of the others propagates -- and the fetch latency disappears from the chain.  (Fetching it BEFORE a
-        // monolithic grid.sync() was slower: the release fence of the arrival waits for the loads in flight.)
-        unsigned int first_c = 0u;
-        while (first_c < ncolors && s_off[first_c] == s_off[first_c + 1]) ++first_c;
-        SweepRec q;
-        q.cs = 0;
-        if (first_c < ncolors && s_off[first_c] + vtid < s_off[first_c + 1]) q = sweep_load(w, s_off[first_c] + vtid);
-        for (int it = 0; it < iterations; ++it)
-            for (unsigned int c = first_c; c < ncolors; ++c) {
-                if (s_off[c] == s_off[c + 1]) continue;
-                const unsigned int s0 = s_off[c] + vtid;
-                if (s0 < s_off[c + 1]) {
-                    if (CS_COUNT(q.cs) != 0) sweep_apply(w, s0, q, gvel2.load(q.b.x), gvel2.load(q.b.y), gvel2);
-                    for (unsigned int s = s0 + nth; s < s_off[c + 1]; s += nth) sweep_one(w, s, gvel2);
-                }
-                auto token = grid.barrier_arrive();
-                // the next non-empty colour (of this sweep, or the first one of the next sweep)
-                unsigned int cn = c + 1u;
-                while (cn < ncolors && s_off[cn] == s_off[cn + 1]) ++cn;
-                const bool more = cn < ncolors || it + 1 < iterations;
-                if (cn >= ncolors) cn = first_c;
-                q.cs = 0;
-                if (more && s_off[cn] + vtid < s_off[cn + 1]) q = sweep_load(w, s_off[cn] + vtid);
-                grid.barrier_wait(std::move(token));
-            }
-    } else if (phases & SV_SWEEP)
+    // ([measured] fetching a thread's NEXT record between the halves of a split grid barrier -- grid.barrier_arrive(), loads,
+    // grid.barrier_wait() -- was bit-identical and no faster either, solve 0.297 -> 0.309 ms at 65k bodies: the phase is
+    // bound by the barrier and the velocity gather that can only start behind it, not by the record fetch)
+    if (phases & SV_SWEEP)
     for (int it = 0; it < iterations; ++it)
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;

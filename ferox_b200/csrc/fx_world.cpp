@@ -710,7 +710,6 @@ static void fill_dev_params(frWorld *w, float dt) {
         if (d.sort_launch > FX_SORT_MAX_PASSES) d.sort_launch = FX_SORT_MAX_PASSES;
     }
     { static const int sq = [] { const char *e = std::getenv("FEROX_COLOR_SQUEEZE"); return e ? std::atoi(e) : 2; }(); d.color_squeeze = sq; }
-    { static const int pf = [] { const char *e = std::getenv("FEROX_SOLVE_PREFETCH"); return e ? std::atoi(e) : 1; }(); d.solve_prefetch = pf; }
     {
         // solver record layout (fx_solve.cu SOL_AT): contact-major once the sweeps are bandwidth-bound
         const bool contact_major = w->force_large || w->manifold_hint >= 400000;
