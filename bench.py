@@ -62,6 +62,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-sub", action="store_true", help="no config1/3/4/5 sub-records (profiling runs)")
     ap.add_argument("--sub-steps", type=int, default=200, help="timed steps of the config4 / config5 sub-records")
+    ap.add_argument("--sub-timeout", type=int, default=420, help="seconds after which the sub-records are abandoned and the line printed without them")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
                     help="config2 (default, the headline): one 65,536-body mixed pile per GPU; config3: one 1M-circle column "
                          "collapse per GPU; config4: 4,096 independent 256-body worlds batched into one launch set and "
@@ -765,13 +766,33 @@ def run_b200(args):
     sc.release()
 
     # ---- sub-records: the other BASELINE configs on the same build, same process (every rank takes part at N > 1) ----
-    if not args.skip_sub and args.workload == "config2":
-        sub = run_sub_records(L, args, rank, world_size, local_rank, dist, barrier)
+    # The headline must survive whatever happens in there: a watchdog prints the line without the unfinished
+    # sub-records and ends the process if they take longer than --sub-timeout seconds (e.g. a rank lost inside a collective).
+    import threading
+    printed = threading.Lock()
+
+    def emit(extra=None):
+        if not printed.acquire(blocking=False):
+            return
         if rank == 0:
-            line.update(sub)
-    if rank == 0:
-        print(json.dumps(line))
-        sys.stdout.flush()
+            if extra:
+                line.update(extra)
+            print(json.dumps(line))
+            sys.stdout.flush()
+
+    def give_up():
+        emit({"sub_records": "not finished within %d s: left out" % args.sub_timeout})
+        os._exit(0)
+
+    if not args.skip_sub and args.workload == "config2":
+        dog = threading.Timer(args.sub_timeout, give_up)
+        dog.daemon = True
+        dog.start()
+        sub = run_sub_records(L, args, rank, world_size, local_rank, dist, barrier)
+        dog.cancel()
+        emit(sub)
+    else:
+        emit()
     barrier()
     if dist is not None:
         dist.destroy_process_group()
