@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
+#include <mutex>
 #include <new>
 
 #include <cuda_profiler_api.h>
@@ -18,14 +20,20 @@
 // errors, device selection
 // ---------------------------------------------------------------------------------------------
 long long g_fx_launches = 0;
-static int g_error = 0;
+// the sticky error is process-wide and may be set from any thread that steps a world (different worlds may be
+// stepped from different threads): first error wins, code and text change together under a lock
+static std::atomic<int> g_error{ 0 };
+static std::mutex g_error_lock;
 static char g_error_text[256] = "no error";
 static thread_local int g_device = -1;
 
 void fx_set_error(int code, const char *what) {
-    if (g_error == 0) {
-        g_error = code;
-        std::snprintf(g_error_text, sizeof g_error_text, "%s", what);
+    {
+        std::lock_guard<std::mutex> hold(g_error_lock);
+        if (g_error.load(std::memory_order_relaxed) == 0) {
+            std::snprintf(g_error_text, sizeof g_error_text, "%s", what);
+            g_error.store(code, std::memory_order_release);
+        }
     }
     std::fprintf(stderr, "[ferox-b200] ERROR %d: %s\n", code, what);
 }
@@ -36,9 +44,18 @@ bool fx_cuda_ok(cudaError_t e, const char *what) {
     fx_set_error(1000 + (int) e, buf);
     return false;
 }
-extern "C" int frxGetLastError(void) { return g_error; }
-extern "C" void frxClearLastError(void) { g_error = 0; g_error_text[0] = 0; }
-extern "C" const char *frxGetLastErrorString(void) { return g_error_text; }
+extern "C" int frxGetLastError(void) { return g_error.load(std::memory_order_acquire); }
+extern "C" void frxClearLastError(void) {
+    std::lock_guard<std::mutex> hold(g_error_lock);
+    g_error.store(0, std::memory_order_release);
+    g_error_text[0] = 0;
+}
+extern "C" const char *frxGetLastErrorString(void) {
+    static thread_local char copy[256];
+    std::lock_guard<std::mutex> hold(g_error_lock);
+    std::snprintf(copy, sizeof copy, "%s", g_error_text);
+    return copy;
+}
 extern "C" int frxSetDevice(int device) {
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return -1;
