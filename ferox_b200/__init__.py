@@ -73,6 +73,7 @@ EXT_PROTOTYPES = {
     "frxGetManifolds": (I, [P, P, I]),
     "frxComputeCollisions": (I, [P, i32p, I, P, P]),
     "frxRaycastBatch": (I, [P, P, I, P, i32p, I]),
+    "frxPointQueryBatch": (I, [P, P, I, i32p, i32p, I]),
     "frxDeviceSinCos": (I, [f32p, I, f32p, f32p]),
     "frxSetProfiling": (None, [P, I]),
     "frxGetStageTimes": (I, [P, C.POINTER(C.c_double)]),

@@ -249,6 +249,44 @@ __global__ void __launch_bounds__(RC_BLOCK) k_raycast_batch(DevWorld w, const Ra
     }
 }
 
+// point queries: which bodies contain each point (frBodyContainsPoint per body, ascending index), a block per point
+__global__ void __launch_bounds__(RC_BLOCK) k_point_query_batch(DevWorld w, const V2 *points, int npoints, int max_hits, int *bodies, int *counts) {
+    __shared__ unsigned int s_run;
+    for (int r = blockIdx.x; r < npoints; r += gridDim.x) {
+        const V2 pt = points[r];
+        if (threadIdx.x == 0) s_run = 0u;
+        __syncthreads();
+        for (int base = 0; base < w.n_owned; base += RC_BLOCK) {
+            const int i = base + (int) threadIdx.x;
+            bool found = false;
+            if (i < w.n_owned) {
+                const int2 sh = w.shape[i];
+                if (sh.x >= 0) {
+                    const ShapeDev *s = &w.shapes[sh.x];
+                    const float4 p = w.posrot[i];
+                    Xf t;
+                    t.p = v2(p.x, p.y); t.sn = p.z; t.cs = p.w;
+                    found = shape_contains_point(s->type, s->radius, s->nv, s->verts, t, pt);
+                }
+            }
+            unsigned int total;
+            const unsigned int excl = block_exclusive_scan<RC_BLOCK>(found ? 1u : 0u, &total);
+            const unsigned int pos = s_run + excl;
+            if (found && (int) pos < max_hits) bodies[(size_t) r * (size_t) max_hits + pos] = i;
+            __syncthreads();
+            if (threadIdx.x == 0) s_run += total;
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) counts[r] = (int) s_run;
+        __syncthreads();
+    }
+}
+void fx_launch_point_query_batch(const DevWorld &w, const FxLaunchCtx &cx, const void *points, int npoints, int max_hits, int *bodies, int *counts) {
+    if (npoints <= 0) return;
+    k_point_query_batch<<<npoints < cx.max_blocks ? npoints : cx.max_blocks, RC_BLOCK, 0, cx.stream>>>(w, (const V2 *) points, npoints, max_hits, bodies, counts);
+    ++g_fx_launches;
+}
+
 void fx_launch_raycast_batch(const DevWorld &w, const FxLaunchCtx &cx, const void *rays, int nrays, int max_hits, void *hits, int *counts) {
     if (nrays <= 0) return;
     k_raycast_batch<<<nrays < cx.max_blocks ? nrays : cx.max_blocks, RC_BLOCK, 0, cx.stream>>>(w, (const RayDev *) rays, nrays, max_hits, (RayHitPod *) hits, counts);

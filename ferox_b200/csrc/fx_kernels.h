@@ -87,6 +87,8 @@ void fx_launch_unpack_collisions(const DevWorld &w, const FxLaunchCtx &cx, const
 // index in the body slot, counts[r] = hits found for ray r (may exceed max_hits)
 void fx_launch_raycast_batch(const DevWorld &w, const FxLaunchCtx &cx, const void *rays, int nrays, int max_hits, void *hits, int *counts);
 
+void fx_launch_point_query_batch(const DevWorld &w, const FxLaunchCtx &cx, const void *points, int npoints, int max_hits, int *bodies, int *counts);
+
 // single-pair / utility entry points (used by the public per-body functions and the tests)
 void fx_launch_collide_pairs(const DevWorld &w, const FxLaunchCtx &cx, const int2 *pairs, int n, Manifold *out);
 

@@ -484,21 +484,16 @@ extern "C" bool frComputeRaycast(const frBody *b, frRay ray, frRaycastHit *hit) 
 
 extern "C" bool frBodyContainsPoint(const frBody *b, frVector2 point) {
     if (b == nullptr) return false;
-    frShapeType type = frGetShapeType(b->shape);
-    frTransform tx = frGetBodyTransform(b);
-    if (type == FR_SHAPE_CIRCLE) {
-        float dx = point.x - tx.position.x, dy = point.y - tx.position.y, r = b->shape->radius;
-        return (dx * dx) + (dy * dy) <= r * r;
-    }
+    const frShape *s = b->shape;
+    const frShapeType type = frGetShapeType(s);
+    if (type != FR_SHAPE_CIRCLE && type != FR_SHAPE_POLYGON) return false;
+    V2 verts[FX_MAX_VERTS] = {};
+    int nv = 0;
     if (type == FR_SHAPE_POLYGON) {
-        frRay ray;
-        ray.origin = point; ray.direction.x = 1.0f; ray.direction.y = 0.0f; ray.maxDistance = FLT_MAX;
-        frRaycastHit h;
-        std::memset(&h, 0, sizeof h);
-        (void) frComputeRaycast(b, ray, &h);
-        return h.inside;
+        nv = s->vertices.count < FX_MAX_VERTS ? s->vertices.count : FX_MAX_VERTS;
+        for (int k = 0; k < nv; ++k) verts[k] = V(s->vertices.data[k]);
     }
-    return false;
+    return shape_contains_point((int) type, s->radius, nv, verts, to_xf(frGetBodyTransform(b)), V(point));
 }
 
 // ================================================================================================

@@ -82,3 +82,19 @@ FX_HD bool ray_vs_shape(int type, float radius, int nv, const V2 *verts, Xf t, V
     }
     return false;
 }
+
+// frBodyContainsPoint (src/rigid_body.c:261-289): a circle by squared distance; a polygon by the parity of the edge
+// crossings of a ray cast along +x from the point (through frComputeRaycast, quirks included)
+FX_HD bool shape_contains_point(int type, float radius, int nv, const V2 *verts, Xf t, V2 point) {
+    if (type == 1) {
+        const float dx = point.x - t.p.x, dy = point.y - t.p.y;
+        return (dx * dx) + (dy * dy) <= radius * radius;
+    }
+    if (type == 2) {
+        RayHitPod hit;
+        hit.body = 0; hit.point = v2(0.f, 0.f); hit.normal = v2(0.f, 0.f); hit.distance = 0.0f; hit.inside = 0;
+        (void) ray_vs_shape(type, radius, nv, verts, t, point, vunit(v2(1.0f, 0.0f)), FLT_MAX, hit);
+        return hit.inside != 0;
+    }
+    return false;
+}

@@ -2240,6 +2240,41 @@ extern "C" int frxRaycastBatch(frWorld *w, const frRay *rays, int nRays, frRayca
     return (int) (total > 0x7fffffff ? 0x7fffffff : total);
 }
 
+extern "C" int frxPointQueryBatch(frWorld *w, const frVector2 *points, int nPoints, int *bodyIndices, int *counts, int maxPerPoint) {
+    if (!w || !points || nPoints <= 0 || !bodyIndices || !counts || maxPerPoint <= 0) return 0;
+    if (!w->device_ok) { fx_set_error(1, "frxPointQueryBatch: world has no CUDA device (no CPU fallback)"); return 0; }
+    for (int r = 0; r < nPoints; ++r) counts[r] = 0;
+    if (w->bodies.empty()) return 0;
+    cudaSetDevice(w->device);
+    ensure_body_capacity(w, (int) w->bodies.size());
+    sync_shapes(w);
+    world_push(w);
+    DevWorld &d = w->dw;
+    d.n_owned = (int) w->bodies.size();
+    d.n = d.n_owned;
+    d.shapes = w->d_shapes;
+    cudaStream_t s = w->stream;
+    void *d_points = nullptr;
+    int *d_idx = nullptr, *d_counts = nullptr;
+    const size_t idx_bytes = (size_t) nPoints * (size_t) maxPerPoint * sizeof(int);
+    if (!fx_cuda_ok(cudaMalloc(&d_points, (size_t) nPoints * sizeof(frVector2)), "cudaMalloc points") ||
+        !fx_cuda_ok(cudaMalloc((void **) &d_idx, idx_bytes), "cudaMalloc indices") ||
+        !fx_cuda_ok(cudaMalloc((void **) &d_counts, (size_t) nPoints * sizeof(int)), "cudaMalloc counts")) {
+        cudaFree(d_points); cudaFree(d_idx); cudaFree(d_counts);
+        return 0;
+    }
+    cudaMemcpyAsync(d_points, points, (size_t) nPoints * sizeof(frVector2), cudaMemcpyHostToDevice, s);
+    fx_launch_point_query_batch(d, w->cx, d_points, nPoints, maxPerPoint, d_idx, d_counts);
+    cudaMemcpyAsync(counts, d_counts, (size_t) nPoints * sizeof(int), cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(bodyIndices, d_idx, idx_bytes, cudaMemcpyDeviceToHost, s);
+    const bool ok = fx_cuda_ok(cudaStreamSynchronize(s), "frxPointQueryBatch");
+    cudaFree(d_points); cudaFree(d_idx); cudaFree(d_counts);
+    if (!ok) return 0;
+    long long total = 0;
+    for (int r = 0; r < nPoints; ++r) total += counts[r];
+    return (int) (total > 0x7fffffff ? 0x7fffffff : total);
+}
+
 // ---------------------------------------------------------------------------------------------
 // world ray cast (reference src/world.c:291-320): one ray through the batched device query
 // ---------------------------------------------------------------------------------------------

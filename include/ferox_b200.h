@@ -337,6 +337,11 @@ int frxGetManifolds(frWorld *w, frxManifold *out, int max);
    the total number of hits found.  frComputeWorldRaycast itself runs through this path. */
 int frxRaycastBatch(frWorld *w, const frRay *rays, int nRays, frRaycastHit *hits, int *counts, int maxHitsPerRay);
 
+/* Point queries on the device state: for point p the world indices of the bodies that contain it -- frBodyContainsPoint
+   (src/rigid_body.c:261-289) evaluated for every body, ascending -- are written to bodyIndices[p * maxPerPoint ...],
+   counts[p] receives how many there are (it may exceed maxPerPoint).  Returns the total. */
+int frxPointQueryBatch(frWorld *w, const frVector2 *points, int nPoints, int *bodyIndices, int *counts, int maxPerPoint);
+
 /* Batched narrow phase on bodies of a world: pairs[2*i], pairs[2*i+1] are world indices; out[i] is
    written only on a hit (like frComputeCollision); hit[i] receives 0/1.  Returns hits. */
 int frxComputeCollisions(frWorld *w, const int *pairs, int nPairs, frCollision *out, int *hit);

@@ -912,3 +912,48 @@ def test_world_raycast_batch_matches_reference_for_thousands_of_rays(gpu, ref):
         L.frComputeWorldRaycast(gs.world, rays[k], cb, None)
         assert len(got) == counts[k]
     rs.release(); gs.release()
+
+
+def test_point_query_batch_matches_reference_contains_point(gpu, ref):
+    """frxPointQueryBatch (device sweep) against the unmodified reference's frBodyContainsPoint evaluated body by body:
+    for 1,500 points in and around a settled mixed pile the same ascending list of containing bodies."""
+    import ctypes as C
+    L = gpu
+    spec = scenes.mixed_pile(400, width=40.0)
+    worlds = []
+    for lib in (ref, L):
+        sc = scenes.Scene(lib, spec, prime=False)
+        if lib is L:
+            lib.frxSetWorldSolverMode(sc.world, fb.SOLVER_SERIAL)
+        lib.frStepWorld(sc.world, DT)
+        sc.step(120)
+        worlds.append(sc)
+    rs, gs = worlds
+    st = gs.snapshot()
+    assert_states_equal(rs.snapshot(), st, "settled pile")
+    rng = np.random.default_rng(9)
+    n = 1500
+    pts = np.empty((n, 2), np.float32)
+    for k in range(n):
+        c = st["pos"][rng.integers(0, spec.n)]
+        pts[k] = (c[0] + rng.normal() * 0.5, c[1] + rng.normal() * 0.5)
+    max_per = 8
+    idx = np.full(n * max_per, -1, np.int32)
+    counts = np.zeros(n, np.int32)
+    total = L.frxPointQueryBatch(gs.world, pts.ctypes.data_as(C.c_void_p), n, idx, counts, max_per)
+    fb.check_error(L)
+    members = [ref.frGetBodyInWorld(rs.world, i) for i in range(ref.frGetBodyCountInWorld(rs.world))]
+    found = 0
+    for k in range(n):
+        p = capi.Vector2(float(pts[k, 0]), float(pts[k, 1]))
+        want = [i for i, b in enumerate(members) if ref.frBodyContainsPoint(b, p)]
+        got = idx[k * max_per:k * max_per + counts[k]].tolist()
+        assert got == want, (k, got, want)
+        found += len(want)
+    assert total == found and found > 400, (total, found)
+    # the host entry point is the same arithmetic
+    for k in range(0, n, 50):
+        p = capi.Vector2(float(pts[k, 0]), float(pts[k, 1]))
+        for i in idx[k * max_per:k * max_per + counts[k]]:
+            assert L.frBodyContainsPoint(L.frGetBodyInWorld(gs.world, int(i)), p)
+    rs.release(); gs.release()
