@@ -206,6 +206,7 @@ const BodyRow fx_row_read(const frBody *b); // current dynamic row (pulls if the
 void fx_world_pull(frWorld *w);
 void fx_world_pull_some(frWorld *w, unsigned want);   // want: FX_DIRTY_POSROT | _ANGLE | _VEL | _AABB
 void fx_world_mark(frWorld *w, unsigned bits);
+void fx_world_mark_body(frWorld *w, int index, unsigned bits);   // as fx_world_mark, for a setter on ONE body (its mirror row is up to date)
 void fx_set_error(int code, const char *what);
 bool fx_cuda_ok(cudaError_t e, const char *what);
 

@@ -247,7 +247,7 @@ static RowRef row_of(frBody *b) {
     }
     return r;
 }
-static inline void mark(frBody *b, unsigned bits) { if (b->world) fx_world_mark(b->world, bits); }
+static inline void mark(frBody *b, unsigned bits) { if (b->world) fx_world_mark_body(b->world, b->index, bits); }
 
 static frTransform tx_of(const RowRef &r) {
     frTransform t;

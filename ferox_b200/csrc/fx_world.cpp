@@ -344,6 +344,26 @@ void fx_world_mark(frWorld *w, unsigned bits) {
     if (bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) { w->extent_unknown = true; w->extent_mark_step = w->steps; }
 }
 
+// A setter on one body: the key width only becomes unknown when the body's new cell rectangle leaves the cell bounds
+// the last completed step measured (a kinematic platform nudged every frame stays inside them: no spare sort passes,
+// no change of the graph key).
+static void read_snapshot(frWorld *w, bool wait);
+void fx_world_mark_body(frWorld *w, int index, unsigned bits) {
+    if ((bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) && w->snapshot_pending) read_snapshot(w, false);   // (a poll, never a wait)
+    if ((bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) && !w->extent_unknown && w->last.key_bits != 0u &&
+        index >= 0 && index < (int) w->bodies.size() && w->cell > 0.0f && !w->snapshot_pending) {
+        const float4 a = w->h.aabb[index];
+        const float inv = 1.0f / w->cell;
+        const int x0 = cell_coord(a.x, inv), y0 = cell_coord(a.y, inv), x1 = cell_coord(a.x + a.z, inv), y1 = cell_coord(a.y + a.w, inv);
+        const StepCountersDev &c = w->last;
+        if (x0 >= c.cell_min_x && y0 >= c.cell_min_y && x1 <= c.cell_max_x && y1 <= c.cell_max_y) {
+            w->dirty |= bits;
+            return;
+        }
+    }
+    fx_world_mark(w, bits);
+}
+
 // bring the pinned host mirror up to date with the device (one bulk D2H per dynamic array)
 // Downloads the arrays of the host mirror that are stale AND wanted.  A step makes all four state arrays stale
 // (and the mirror's force accumulators, which the step cleared on the device).
