@@ -269,17 +269,22 @@ def hbm_peak():
 
 
 def ncu_traffic(csv_name, kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, one launch) of `kernel` from a committed ncu capture."""
+    """dram__bytes_read.sum + dram__bytes_write.sum (bytes, one launch) of `kernel` from a committed ncu capture
+    (profiles/summarize.py layout: a header row, a unit row, one row per launch)."""
     cap = os.path.join(ROOT, "profiles", csv_name)
     if not os.path.exists(cap):
         return None, None
-    for row in open(cap):
-        f = row.strip().split(",")
-        if kernel in f[0]:
-            try:
-                return (float(f[2]) + float(f[3])) * 1e6, "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, one launch)" % csv_name
-            except (ValueError, IndexError):
-                continue
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    rows = [r.rstrip("\n").split(",") for r in open(cap)]
+    try:
+        hdr, unit = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        for f in rows[2:]:
+            if kernel in f[0]:
+                return (float(f[ir]) * scale[unit[ir]] + float(f[iw]) * scale[unit[iw]],
+                        "profiles/%s (dram__bytes_read.sum + dram__bytes_write.sum, one launch)" % csv_name)
+    except (ValueError, IndexError, KeyError):
+        pass
     return None, None
 
 
@@ -712,7 +717,9 @@ def run_b200(args):
             if kind > 0:
                 traffic, traffic_src = ncu_traffic("r02_config2_top_kernels_ncu.csv", "k_sweep_cluster")
             else:
-                traffic, traffic_src = ncu_traffic("r01_end_top_kernels_ncu.csv", "k_solve_colored")
+                traffic, traffic_src = ncu_traffic("r02_config2_top_kernels_ncu.csv", "k_solve_colored")
+                if traffic is None:
+                    traffic, traffic_src = ncu_traffic("r01_end_top_kernels_ncu.csv", "k_solve_colored")
         if strips:
             # the strip step runs the solver as 12 separately launched stages with an exchange after each; there
             # are no per-stage events, so the roofline line is the WHOLE step of this rank's strip
