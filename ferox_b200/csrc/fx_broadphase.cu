@@ -302,6 +302,9 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_hist(SortJob job) {
 #define DS_PFX (2u << 30)
 #define DS_VAL ((1u << 30) - 1u)
 
+// WIDE: keys of more than 32 bits (the host launches this build only when it launches more than four digit passes;
+// the narrow build keeps the high words out of its registers: 64 instead of 80, one more resident block per SM)
+template <bool WIDE>
 __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
     __shared__ unsigned int s_wc[BP_BLOCK / 32][256];   // per-warp digit counters -> exclusive bases
     __shared__ unsigned int s_gb[256];                  // global base per digit for this tile
@@ -309,12 +312,12 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
     const unsigned int passes = job.passes_dev ? *job.passes_dev : job.passes;
     if ((unsigned int) pass >= passes) return;
     // wide keys (> 32 bits): the high words travel with the entries; passes 4..7 take their digit from them
-    const bool wide = job.bits_dev != nullptr && *job.bits_dev > 32u;
+    const bool wide = WIDE && job.bits_dev != nullptr && *job.bits_dev > 32u;
     const unsigned int *kin = job.keys[pass & 1], *vin = job.vals[pass & 1];
     unsigned int *kout = job.keys[(pass + 1) & 1], *vout = job.vals[(pass + 1) & 1];
     const unsigned int *hin = wide ? job.keys_hi[pass & 1] : nullptr;
     unsigned int *hout = wide ? job.keys_hi[(pass + 1) & 1] : nullptr;
-    const bool hi_digit = pass >= 4;
+    const bool hi_digit = WIDE && pass >= 4;
     unsigned int *dstatus = job.dstatus + (size_t) pass * job.dstatus_stride;
     unsigned int *ticket = job.tickets + pass;
     const unsigned int shift = 8u * (unsigned int) (pass & 3);
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
             unsigned int e = base + j * 32 + lane;
             bool ok = e < n;
             key[j] = ok ? kin[e] : 0xffffffffu;
-            khi[j] = (ok && wide) ? hin[e] : 0u;
+            khi[j] = (WIDE && ok && wide) ? hin[e] : 0u;
             val[j] = ok ? vin[e] : 0u;
             unsigned int d = ((hi_digit ? khi[j] : key[j]) >> shift) & 255u;
             unsigned int m = ok ? d : (256u + lane);
@@ -383,7 +386,7 @@ __global__ void __launch_bounds__(BP_BLOCK) k_sort_pass(SortJob job, int pass) {
                 unsigned int dd = ((hi_digit ? khi[j] : key[j]) >> shift) & 255u;
                 unsigned int pos = s_gb[dd] + s_wc[warp][dd] + rank[j];
                 kout[pos] = key[j];
-                if (wide) hout[pos] = khi[j];
+                if (WIDE && wide) hout[pos] = khi[j];
                 vout[pos] = val[j];
             }
         }
@@ -395,7 +398,11 @@ static void launch_sort(const SortJob &job, long long cap, int max_passes, int m
     int gridh = (int) (gh < 1 ? 1 : (gh > max_blocks ? max_blocks : gh));
     int gridp = (int) (gp < 1 ? 1 : (gp > max_blocks ? max_blocks : gp));
     if (with_hist) { k_sort_hist<<<gridh, BP_BLOCK, 0, s>>>(job); ++g_fx_launches; }
-    for (int p = 0; p < max_passes; ++p) { k_sort_pass<<<gridp, BP_BLOCK, 0, s>>>(job, p); ++g_fx_launches; }
+    for (int p = 0; p < max_passes; ++p) {
+        if (max_passes > 4) k_sort_pass<true><<<gridp, BP_BLOCK, 0, s>>>(job, p);
+        else k_sort_pass<false><<<gridp, BP_BLOCK, 0, s>>>(job, p);
+        ++g_fx_launches;
+    }
 }
 
 // ---- lexicographic (i, j) ordering of the candidate list: serial / parity mode only -------------

@@ -214,3 +214,33 @@ def test_default_capacity_is_the_reference_macro(gpu):
     assert not L.frAddBodyToWorld(w, L.frCreateBodyFromShape(capi.BODY_DYNAMIC, capi.Vector2(0, 0), c))
     assert L.frxGetWorldCapacity(w) == 2048
     fb.check_error(L)
+
+
+def test_body_moved_by_a_setter_every_frame_keeps_the_graph_and_the_reference_trajectory(gpu, ref):
+    """A kinematic platform nudged with frSetBodyPosition before EVERY step (what reference programs do, e.g.
+    examples/src/cows.c): no sizing pre-pass (a blocking extra broadphase per step in round 1), the captured graph of the
+    step keeps being replayed, and in reference order the trajectory equals the unmodified reference bit for bit
+    (frSetBodyPosition's absolute AABB shift, App. A.9, included)."""
+    L = gpu
+    base = scenes.mixed_pile(300, width=30.0)
+    spec = scenes.SceneSpec(name="platform", cell=base.cell, shapes=list(base.shapes) + [scenes.ShapeSpec("rect", (6.0, 1.0))])
+    scenes._finish(spec, np.concatenate([base.body_type, [capi.BODY_KINEMATIC]]), np.concatenate([base.body_shape, [len(base.shapes)]]),
+                   np.concatenate([base.pos, [[15.0, -30.0]]]), np.concatenate([base.angle, [0.0]]))
+    runs = []
+    for lib, mode in ((ref, None), (L, fb.SOLVER_SERIAL), (L, fb.SOLVER_COLORED)):
+        sc = scenes.Scene(lib, spec, prime=False)
+        if mode is not None:
+            lib.frxSetWorldSolverMode(sc.world, mode)
+        lib.frStepWorld(sc.world, DT)
+        plat = sc.bodies[-1]
+        for s in range(240):
+            lib.frSetBodyPosition(plat, capi.Vector2(15.0 + 4.0 * float(np.sin(0.05 * s)), -30.0 + 0.02 * s))
+            lib.frStepWorld(sc.world, DT)
+        runs.append((sc, scenes.snapshot(lib, sc.bodies)))
+    fb.check_error(L)
+    for k in ("pos", "angle", "vel", "omega"):
+        assert runs[0][1][k].tobytes() == runs[1][1][k].tobytes(), k
+    assert L.frxGetGraphReplays(runs[2][0].world) >= 200
+    assert np.isfinite(runs[2][1]["pos"]).all()
+    for sc, _ in runs:
+        sc.release()
