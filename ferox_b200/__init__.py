@@ -53,6 +53,7 @@ EXT_PROTOTYPES = {
     "frxStripInitNccl": (I, [P, I, I, P]),
     "frxStripStep": (None, [C.POINTER(C.c_void_p), I, F]),
     "frxStripMigrate": (I, [C.POINTER(C.c_void_p), I]),
+    "frxStripGetTransport": (I, [P]),
     "frxSetWorldSolverMode": (None, [P, I]),
     "frxGetWorldSolverMode": (I, [P]),
     "frxSetWorldTimestamp": (None, [P, F]),

@@ -164,6 +164,15 @@ struct frWorld_ {
         cudaEvent_t sent = nullptr;                  // my copies into the neighbours' receive buffers are done
         cudaEvent_t consumed = nullptr;              // I have read my receive buffers (neighbours may overwrite them)
         bool ghosts_primed = false;
+        // Receive side: ONE allocation ("inbox") = flag words + the ghost-row buffer + two parities of the per-stage
+        // buffers; recv_full / recv_vel / recv_delta above point into it.  With NCCL neighbours the inbox is also
+        // exported through a CUDA IPC handle and the neighbours' inboxes are mapped here (peer-direct transport).
+        unsigned char *inbox = nullptr;
+        float4 *recv_vel_buf[2] = { nullptr, nullptr }, *recv_delta_buf[2] = { nullptr, nullptr };
+        unsigned char *peer_inbox[2] = { nullptr, nullptr };   // [left, right] neighbours' inboxes, mapped (nullptr: NCCL / in-process)
+        bool peer_direct = false;
+        unsigned int epoch_rows = 0, epoch_stage = 0;          // exchange rounds so far (the same on every rank)
+        unsigned int *push_done = nullptr;                     // [4] "last block" counters of the push kernels
         // ownership migration (frxStripMigrate): rows that change rank travel through these (NCCL neighbours only)
         unsigned char *mig_send[2] = { nullptr, nullptr }, *mig_recv[2] = { nullptr, nullptr };      // device, [left, right]
         unsigned char *mig_hsend[2] = { nullptr, nullptr }, *mig_hrecv[2] = { nullptr, nullptr };    // pinned host

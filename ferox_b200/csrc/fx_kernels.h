@@ -107,6 +107,11 @@ void fx_launch_strip_stage_begin(const DevWorld &w, const FxLaunchCtx &cx, float
 void fx_launch_strip_stage_pack(const DevWorld &w, const FxLaunchCtx &cx, const float4 *ghost_before, const unsigned int *ghost_split, float4 *delta,
                                 const unsigned int *ghost_cnt, const unsigned char *full_msg, const unsigned int *border_idx,
                                 const float4 *border_before, const unsigned int *border_split, float4 *border_vel, unsigned int capacity);
+// peer-direct transport: count-sized copy into the neighbour's mapped inbox + flag; wait for the flag(s) on the receiving stream
+void fx_launch_strip_push(const FxLaunchCtx &cx, const void *src, void *dst, const unsigned int *count_ptr, unsigned int header_q, unsigned int q_per_item,
+                          unsigned int max_items, unsigned int *done, unsigned int *peer_flag, unsigned int epoch);
+void fx_launch_strip_wait(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *flag_a, unsigned int epoch_a, const unsigned int *flag_b,
+                          unsigned int epoch_b, unsigned int *dead);
 void fx_launch_strip_stage_apply(const DevWorld &w, const FxLaunchCtx &cx, const unsigned char *full_msg, const unsigned int *border_idx,
                                  const float4 *recv_delta, const float4 *recv_vel, const float4 *my_delta, const unsigned int *ghost_cnt,
                                  float4 *ghost_before, float4 *border_before, unsigned int capacity);

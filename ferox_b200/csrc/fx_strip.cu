@@ -199,6 +199,54 @@ __global__ void k_strip_stage_apply(DevWorld w, const unsigned char *full_msg, c
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Peer-direct transport (one process per GPU, NVLink): instead of handing a message to ncclSend / ncclRecv, the
+// sender's kernel STORES it straight into the neighbour's receive buffer (the neighbour's "inbox" allocation, mapped
+// into this process through a CUDA IPC handle) and then raises a flag word in the same inbox; the receiver's stream
+// runs a one-thread kernel that waits for the flag before the kernels that read the buffer.  Messages are count-sized
+// (the count lives on the device), one launch per direction, no collective call on the step's critical path.
+//   ordering   every block fences its stores system-wide, the LAST block to finish raises the flag (release);
+//              the waiter polls with acquire loads at system scope
+//   reuse      the per-stage buffers alternate by round parity: round e + 2 overwrites what round e used only after
+//              the neighbour's round e + 1 message has arrived, which it sent after consuming round e
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(ST_BLOCK) k_strip_push(const uint4 *src, uint4 *dst, const unsigned int *count_ptr, unsigned int header_q,
+                                                         unsigned int q_per_item, unsigned int max_items, unsigned int *done,
+                                                         unsigned int *peer_flag, unsigned int epoch) {
+    const unsigned int items = min(*count_ptr, max_items);
+    const unsigned int total = header_q + items * q_per_item;
+    for (unsigned int q = blockIdx.x * blockDim.x + threadIdx.x; q < total; q += gridDim.x * blockDim.x) dst[q] = src[q];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(done, 1u) == gridDim.x - 1u) {
+        *done = 0u;
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer_flag), "r"(epoch) : "memory");
+    }
+}
+
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// waits until the flag(s) have reached their epochs.  A lost neighbour must not hang the GPU: after 30 s the waiter gives
+// up, reports it (overflow bit 64) and latches `*dead`, which makes every later wait of this strip return at once.
+__global__ void k_strip_wait(DevWorld w, const unsigned int *flag_a, unsigned int epoch_a, const unsigned int *flag_b, unsigned int epoch_b,
+                             unsigned int *dead) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (*dead) { atomicOr(&w.ctr->overflow, 64u); return; }
+    unsigned long long t0, t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        const bool a = flag_a == nullptr || (int) (ld_acquire_sys(flag_a) - epoch_a) >= 0;
+        const bool b = flag_b == nullptr || (int) (ld_acquire_sys(flag_b) - epoch_b) >= 0;
+        if (a && b) return;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > 30000000000ull) { *dead = 1u; atomicOr(&w.ctr->overflow, 64u); return; }
+    }
+}
+
 static inline int grid_for(long long n, int block, int max_blocks) {
     long long g = (n + block - 1) / block;
     if (g < 1) g = 1;
@@ -252,5 +300,18 @@ void fx_launch_strip_stage_apply(const DevWorld &w, const FxLaunchCtx &cx, const
                                  float4 *ghost_before, float4 *border_before, unsigned int capacity) {
     k_strip_stage_apply<<<grid_for(capacity, ST_BLOCK, cx.max_blocks), ST_BLOCK, 0, cx.stream>>>(w, full_msg, border_idx, recv_delta, recv_vel, my_delta, ghost_cnt,
                                                                                             ghost_before, border_before);
+    ++g_fx_launches;
+}
+
+void fx_launch_strip_push(const FxLaunchCtx &cx, const void *src, void *dst, const unsigned int *count_ptr, unsigned int header_q, unsigned int q_per_item,
+                          unsigned int max_items, unsigned int *done, unsigned int *peer_flag, unsigned int epoch) {
+    const long long total = (long long) header_q + (long long) max_items * q_per_item;
+    int g = grid_for(total, ST_BLOCK, 32);           // small messages: a few blocks keep the "last block" hand-off short
+    k_strip_push<<<g, ST_BLOCK, 0, cx.stream>>>((const uint4 *) src, (uint4 *) dst, count_ptr, header_q, q_per_item, max_items, done, peer_flag, epoch);
+    ++g_fx_launches;
+}
+void fx_launch_strip_wait(const DevWorld &w, const FxLaunchCtx &cx, const unsigned int *flag_a, unsigned int epoch_a, const unsigned int *flag_b,
+                          unsigned int epoch_b, unsigned int *dead) {
+    k_strip_wait<<<1, 32, 0, cx.stream>>>(w, flag_a, epoch_a, flag_b, epoch_b, dead);
     ++g_fx_launches;
 }

@@ -188,8 +188,10 @@ static void world_free_device(frWorld *w) {
     cudaFree(w->lex.keys[0]); cudaFree(w->lex.keys[1]); cudaFree(w->lex.vals[0]); cudaFree(w->lex.vals[1]);
     cudaFree(w->lex.tmp); cudaFree(w->lex.zero_base);
     cudaFree(w->so.r_key); cudaFree(w->so.r_len); cudaFree(w->so.t_key); cudaFree(w->so.t_val);
-    cudaFree(w->strip.send_full); cudaFree(w->strip.recv_full); cudaFree(w->strip.send_vel); cudaFree(w->strip.recv_vel);
-    cudaFree(w->strip.send_delta); cudaFree(w->strip.recv_delta); cudaFree(w->strip.ghost_before); cudaFree(w->strip.border_before);
+    for (int side = 0; side < 2; ++side)
+        if (w->strip.peer_inbox[side]) cudaIpcCloseMemHandle(w->strip.peer_inbox[side]);
+    cudaFree(w->strip.send_full); cudaFree(w->strip.inbox); cudaFree(w->strip.send_vel); cudaFree(w->strip.push_done);
+    cudaFree(w->strip.send_delta); cudaFree(w->strip.ghost_before); cudaFree(w->strip.border_before);
     cudaFree(w->strip.ghost_split); cudaFree(w->strip.border_split);
     cudaFree(w->strip.border_idx); cudaFree(w->strip.ghost_cnt);
     for (int side = 0; side < 2; ++side) {
@@ -222,6 +224,7 @@ static void world_free_device(frWorld *w) {
 
 static void detach_body(frWorld *w, frBody *b);
 static void attach_body(frWorld *w, frBody *b);
+static void strip_map_neighbour_inboxes(frWorld *w);
 void fx_strip_release_comm(frWorld *w);
 static void fx_strip_abort_comm(frWorld *w);
 
@@ -785,7 +788,7 @@ static void read_snapshot(frWorld *w, bool wait) {
         char buf[260];
         std::snprintf(buf, sizeof buf,
                       "device buffer overflow in step %lld (mask 0x%x: 1 cell entries, 2 candidates, 4 manifolds, 8 colours, 16 "
-                      "cell-key range, 32 ghost rows); work was dropped",
+                      "cell-key range, 32 ghost rows, 64 a neighbouring strip never delivered a message); work was dropped",
                       w->steps, w->last.overflow);
         fx_set_error(2, buf);
     }
@@ -1156,6 +1159,7 @@ struct NcclApi {
     int (*GroupEnd)() = nullptr;
     int (*CommDestroy)(void *) = nullptr;
     int (*CommAbort)(void *) = nullptr;
+    int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 };
 NcclApi g_nccl;
@@ -1173,6 +1177,7 @@ bool nccl_load() {
     *(void **) &g_nccl.GroupEnd = dlsym(h, "ncclGroupEnd");
     *(void **) &g_nccl.CommDestroy = dlsym(h, "ncclCommDestroy");
     *(void **) &g_nccl.CommAbort = dlsym(h, "ncclCommAbort");
+    *(void **) &g_nccl.AllReduce = dlsym(h, "ncclAllReduce");
     *(void **) &g_nccl.GetErrorString = dlsym(h, "ncclGetErrorString");
     return g_nccl.GetUniqueId && g_nccl.CommInitRank && g_nccl.Send && g_nccl.Recv && g_nccl.GroupStart && g_nccl.GroupEnd;
 }
@@ -1185,6 +1190,12 @@ bool nccl_ok(int rc, const char *what) {
 }
 size_t full_bytes(const frWorld *w) { return FX_MSG_HEADER + (size_t) w->strip.ghost_cap * sizeof(GhostRow); }
 size_t vel_bytes(const frWorld *w) { return (size_t) w->strip.ghost_cap * sizeof(float4); }
+// inbox layout (identical on every strip of a decomposition: same ghost capacity)
+enum { INBOX_FLAG_ROWS = 0, INBOX_FLAG_VEL = 1, INBOX_FLAG_DELTA = 2, INBOX_FLAGS_BYTES = 256 };
+size_t inbox_off_full(const frWorld *) { return INBOX_FLAGS_BYTES; }
+size_t inbox_off_vel(const frWorld *w, int parity) { return INBOX_FLAGS_BYTES + full_bytes(w) + (size_t) parity * vel_bytes(w); }
+size_t inbox_off_delta(const frWorld *w, int parity) { return INBOX_FLAGS_BYTES + full_bytes(w) + (size_t) (2 + parity) * vel_bytes(w); }
+size_t inbox_bytes(const frWorld *w) { return INBOX_FLAGS_BYTES + full_bytes(w) + 4 * vel_bytes(w); }
 }   // namespace
 
 extern "C" int frxStripGetNcclUniqueId(void *out128) {
@@ -1202,11 +1213,10 @@ extern "C" int frxStripConfigure(frWorld *w, float cutLo, float cutHi, float mar
     st.ghost_cap = (unsigned int) ghostCapacity;
     st.uid_base = uidBase; st.uid_space = uidSpace;
     bool ok = fx_cuda_ok(cudaMalloc((void **) &st.send_full, full_bytes(w)), "cudaMalloc strip") &&
-              fx_cuda_ok(cudaMalloc((void **) &st.recv_full, full_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.inbox, inbox_bytes(w)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.push_done, 4 * sizeof(unsigned int)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.send_vel, vel_bytes(w)), "cudaMalloc strip") &&
-              fx_cuda_ok(cudaMalloc((void **) &st.recv_vel, vel_bytes(w)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.send_delta, vel_bytes(w)), "cudaMalloc strip") &&
-              fx_cuda_ok(cudaMalloc((void **) &st.recv_delta, vel_bytes(w)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.ghost_before, vel_bytes(w)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.border_before, vel_bytes(w)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.ghost_split, (size_t) st.ghost_cap * sizeof(unsigned int)), "cudaMalloc strip") &&
@@ -1214,12 +1224,18 @@ extern "C" int frxStripConfigure(frWorld *w, float cutLo, float cutHi, float mar
               fx_cuda_ok(cudaMalloc((void **) &st.border_idx, (size_t) st.ghost_cap * sizeof(unsigned int)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.ghost_cnt, sizeof(unsigned int)), "cudaMalloc strip");
     if (ok) {
+        st.recv_full = st.inbox + inbox_off_full(w);
+        for (int par = 0; par < 2; ++par) {
+            st.recv_vel_buf[par] = reinterpret_cast<float4 *>(st.inbox + inbox_off_vel(w, par));
+            st.recv_delta_buf[par] = reinterpret_cast<float4 *>(st.inbox + inbox_off_delta(w, par));
+        }
+        st.recv_vel = st.recv_vel_buf[0];
+        st.recv_delta = st.recv_delta_buf[0];
         cudaMemsetAsync(st.send_full, 0, full_bytes(w), w->stream);
-        cudaMemsetAsync(st.recv_full, 0, full_bytes(w), w->stream);     // count 0 until a neighbour writes
+        cudaMemsetAsync(st.inbox, 0, inbox_bytes(w), w->stream);        // flags 0, ghost count 0 until a neighbour writes
+        cudaMemsetAsync(st.push_done, 0, 4 * sizeof(unsigned int), w->stream);
         cudaMemsetAsync(st.send_vel, 0, vel_bytes(w), w->stream);
-        cudaMemsetAsync(st.recv_vel, 0, vel_bytes(w), w->stream);
         cudaMemsetAsync(st.send_delta, 0, vel_bytes(w), w->stream);
-        cudaMemsetAsync(st.recv_delta, 0, vel_bytes(w), w->stream);
         cudaMemsetAsync(st.ghost_cnt, 0, sizeof(unsigned int), w->stream);
         cudaMemsetAsync(st.ghost_split, 0, (size_t) st.ghost_cap * sizeof(unsigned int), w->stream);
         cudaMemsetAsync(st.border_split, 0, (size_t) st.ghost_cap * sizeof(unsigned int), w->stream);
@@ -1268,6 +1284,59 @@ static void fx_strip_abort_comm(frWorld *w) {
     fx_set_error(7, "strip step failed after its first exchange: the NCCL communicator was aborted");
 }
 
+// Peer-direct transport set-up (collective over the communicator): every rank exports its inbox through a CUDA IPC handle,
+// trades handles with its neighbours over NCCL, maps theirs, and the ranks agree (all-reduce MIN) whether EVERY mapping
+// worked; only then do the per-stage exchanges bypass NCCL.  FEROX_STRIP_PEER=0 keeps NCCL send/recv.
+static void strip_map_neighbour_inboxes(frWorld *w) {
+    frWorld_::Strip &st = w->strip;
+    const char *env = std::getenv("FEROX_STRIP_PEER");
+    const bool want = !(env && std::atoi(env) == 0) && g_nccl.AllReduce != nullptr;
+    cudaStream_t s = w->stream;
+    const int left = st.rank - 1, right = st.rank + 1;
+    unsigned char *dbuf = nullptr;                       // [mine 64][from left 64][from right 64][ok 4][all ok 4]
+    if (!fx_cuda_ok(cudaMalloc((void **) &dbuf, 256), "cudaMalloc ipc")) return;
+    cudaIpcMemHandle_t mine, theirs[2];
+    std::memset(&mine, 0, sizeof mine);
+    int ok = (want && cudaIpcGetMemHandle(&mine, st.inbox) == cudaSuccess) ? 1 : 0;
+    (void) cudaGetLastError();
+    cudaMemcpyAsync(dbuf, &mine, 64, cudaMemcpyHostToDevice, s);
+    g_nccl.GroupStart();
+    if (left >= 0) { g_nccl.Send(dbuf, 64, 0, left, st.nccl_comm, s); g_nccl.Recv(dbuf + 64, 64, 0, left, st.nccl_comm, s); }
+    if (right < st.nranks) { g_nccl.Send(dbuf, 64, 0, right, st.nccl_comm, s); g_nccl.Recv(dbuf + 128, 64, 0, right, st.nccl_comm, s); }
+    nccl_ok(g_nccl.GroupEnd(), "ncclGroupEnd (ipc handles)");
+    cudaMemcpyAsync(&theirs[0], dbuf + 64, 64, cudaMemcpyDeviceToHost, s);
+    cudaMemcpyAsync(&theirs[1], dbuf + 128, 64, cudaMemcpyDeviceToHost, s);
+    if (!fx_cuda_ok(cudaStreamSynchronize(s), "ipc handle exchange")) ok = 0;
+    void *mapped[2] = { nullptr, nullptr };
+    if (ok) {
+        if (left >= 0 && cudaIpcOpenMemHandle(&mapped[0], theirs[0], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+        if (right < st.nranks && cudaIpcOpenMemHandle(&mapped[1], theirs[1], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) ok = 0;
+        (void) cudaGetLastError();
+    }
+    int all_ok = 0;
+    if (g_nccl.AllReduce != nullptr) {
+        cudaMemcpyAsync(dbuf + 192, &ok, sizeof(int), cudaMemcpyHostToDevice, s);
+        nccl_ok(g_nccl.AllReduce(dbuf + 192, dbuf + 196, 1, /* ncclInt32 */ 2, /* ncclMin */ 3, st.nccl_comm, s), "ncclAllReduce (peer-direct vote)");
+        cudaMemcpyAsync(&all_ok, dbuf + 196, sizeof(int), cudaMemcpyDeviceToHost, s);
+        if (!fx_cuda_ok(cudaStreamSynchronize(s), "peer-direct vote")) all_ok = 0;
+    }
+    cudaFree(dbuf);
+    if (all_ok) {
+        st.peer_inbox[0] = (unsigned char *) mapped[0];
+        st.peer_inbox[1] = (unsigned char *) mapped[1];
+        st.peer_direct = true;
+    } else {
+        for (int side = 0; side < 2; ++side)
+            if (mapped[side]) cudaIpcCloseMemHandle(mapped[side]);
+        (void) cudaGetLastError();
+    }
+}
+
+extern "C" int frxStripGetTransport(const frWorld *w) {
+    if (!w || !w->strip.enabled) return -1;
+    return w->strip.nccl_comm ? (w->strip.peer_direct ? 2 : 1) : 0;
+}
+
 extern "C" int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *uniqueId128) {
     if (!w || !w->strip.enabled || !uniqueId128 || !nccl_load()) return -1;
     cudaSetDevice(w->device);
@@ -1275,7 +1344,9 @@ extern "C" int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *un
     std::memcpy(&id, uniqueId128, sizeof id);
     w->strip.rank = rank;
     w->strip.nranks = nranks;
-    return nccl_ok(g_nccl.CommInitRank(&w->strip.nccl_comm, nranks, id, rank), "ncclCommInitRank") ? 0 : -1;
+    if (!nccl_ok(g_nccl.CommInitRank(&w->strip.nccl_comm, nranks, id, rank), "ncclCommInitRank")) return -1;
+    strip_map_neighbour_inboxes(w);
+    return 0;
 }
 
 // one exchange round for all local strips.  kind 0: border bodies go LEFT.  kind 1: border
@@ -1288,7 +1359,34 @@ static void strip_exchange(frWorld **ws, int n, int kind) {
         const size_t bytes = kind == 0 ? full_bytes(w) : vel_bytes(w);
         const void *to_left = kind == 0 ? (const void *) st.send_full : (const void *) st.send_vel;
         void *from_right = kind == 0 ? (void *) st.recv_full : (void *) st.recv_vel;
-        if (st.nccl_comm) {
+        if (st.nccl_comm && st.peer_direct) {
+            // stores over NVLink straight into the neighbours' inboxes, count-sized, then their flags; my own readers wait
+            // for the flags my neighbours raise here
+            const bool has_left = st.rank > 0, has_right = st.rank + 1 < st.nranks;
+            unsigned int *my_flags = reinterpret_cast<unsigned int *>(st.inbox);
+            const unsigned int *border_count = reinterpret_cast<const unsigned int *>(st.send_full);
+            if (kind == 0) {
+                const unsigned int e = ++st.epoch_rows;
+                if (has_left)
+                    fx_launch_strip_push(w->cx, st.send_full, st.peer_inbox[0] + inbox_off_full(w), border_count, FX_MSG_HEADER / 16,
+                                         (unsigned int) (sizeof(GhostRow) / 16), st.ghost_cap, st.push_done + 0,
+                                         reinterpret_cast<unsigned int *>(st.peer_inbox[0]) + INBOX_FLAG_ROWS, e);
+                if (has_right) fx_launch_strip_wait(w->dw, w->cx, my_flags + INBOX_FLAG_ROWS, e, nullptr, 0u, st.push_done + 3);
+            } else {
+                const unsigned int e = ++st.epoch_stage;
+                const int par = (int) (e & 1u);
+                st.recv_vel = st.recv_vel_buf[par];
+                st.recv_delta = st.recv_delta_buf[par];
+                if (has_left)
+                    fx_launch_strip_push(w->cx, st.send_vel, st.peer_inbox[0] + inbox_off_vel(w, par), border_count, 0u, 1u, st.ghost_cap,
+                                         st.push_done + 1, reinterpret_cast<unsigned int *>(st.peer_inbox[0]) + INBOX_FLAG_VEL, e);
+                if (has_right)
+                    fx_launch_strip_push(w->cx, st.send_delta, st.peer_inbox[1] + inbox_off_delta(w, par), st.ghost_cnt, 0u, 1u, st.ghost_cap,
+                                         st.push_done + 2, reinterpret_cast<unsigned int *>(st.peer_inbox[1]) + INBOX_FLAG_DELTA, e);
+                fx_launch_strip_wait(w->dw, w->cx, has_right ? my_flags + INBOX_FLAG_VEL : nullptr, e, has_left ? my_flags + INBOX_FLAG_DELTA : nullptr, e,
+                                     st.push_done + 3);
+            }
+        } else if (st.nccl_comm) {
             const int left = st.rank - 1, right = st.rank + 1;
             g_nccl.GroupStart();
             if (left >= 0) g_nccl.Send(to_left, bytes, /* ncclChar */ 0, left, st.nccl_comm, w->stream);

@@ -312,6 +312,11 @@ int frxStripLinkLocal(frWorld *left, frWorld *right);
 int frxStripGetNcclUniqueId(void *out128);
 int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *uniqueId128);
 void frxStripStep(frWorld **worlds, int nLocal, float dt);
+/* how this strip talks to its neighbours: 0 in-process links (copies between worlds of this process), 1 NCCL send/recv,
+   2 peer-direct (the default across processes when every rank could map its neighbours' receive buffers through CUDA
+   IPC: messages are stored straight into the neighbour's buffer over NVLink by the sender's kernel and announced with a
+   flag; FEROX_STRIP_PEER=0 keeps NCCL); -1 not a strip */
+int frxStripGetTransport(const frWorld *w);
 /* Ownership migration.  Every non-static body whose position has left its strip's x-interval by more than a quarter of
    the margin changes owner: it is removed from its strip and added to the neighbour on that side, with its state
    (transform, velocities, accumulated forces) intact; its contacts are found again by the new owner's next step (their

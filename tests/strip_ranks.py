@@ -59,6 +59,7 @@ def main():
     cuts = [args.width * (k + 1) / world for k in range(world - 1)]
     ss = scenes.StripScene(L, spec, cuts=cuts, margin=args.margin, ghost_cap=args.ghost_cap, rank=rank, devices={rank: local})
     assert L.frxStripInitNccl(ss.worlds[0], rank, world, uid_bytes) == 0, L.frxGetLastErrorString()
+    transport = L.frxStripGetTransport(ss.worlds[0])
     ss.step(1)
     L.frxSynchronizeWorld(ss.worlds[0])
     dist.barrier()
@@ -105,7 +106,7 @@ def main():
                           "max_y": float(ymax.item()), "ke": s[2] / s[1],
                           "ke_single": float((want["vel"][dyn].astype(np.float64) ** 2).sum(1).mean()),
                           "manifolds": int(s[3]), "manifolds_single": int(wc["manifolds"]), "overflow": int(s[4]),
-                          "finite": int(s[5]) == world, "migrated": int(s[6]), "stray_ranks": int(s[7])}), flush=True)
+                          "finite": int(s[5]) == world, "migrated": int(s[6]), "stray_ranks": int(s[7]), "transport": transport}), flush=True)
     dist.barrier()
     dist.destroy_process_group()
 

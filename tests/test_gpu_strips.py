@@ -92,18 +92,21 @@ def test_two_and_three_strips_through_a_pile_match_the_single_world_statisticall
         ss.release()
 
 
-def test_two_strips_on_two_gpus_over_nccl(gpu):
-    """One process per GPU, the library's own NCCL send/recv between neighbours (tests/strip_ranks.py)."""
+@pytest.mark.parametrize("peer", ["1", "0"], ids=["peer_direct", "nccl_send_recv"])
+def test_two_strips_on_two_gpus_over_nccl(gpu, peer):
+    """One process per GPU (tests/strip_ranks.py), both transports: peer-direct (messages stored straight into the
+    neighbour's IPC-mapped receive buffer over NVLink and announced with a flag) and the library's NCCL send/recv."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(root, "tests", "strip_ranks.py"), "--bodies", "3000", "--steps", "600"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root, env=dict(os.environ, FEROX_STRIP_PEER=peer))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     r = json.loads(line)
+    assert r["transport"] == (2 if peer == "1" else 1), r
     assert r["finite"] and r["overflow"] == 0 and r["bodies"] == r["dynamic"], r
     assert abs(r["mean_y"] - r["mean_y_single"]) < 0.02 * abs(r["mean_y_single"]) + 0.05, r
     assert r["max_y"] < 0.6 and r["ke"] < 4.0 * r["ke_single"] + 1.0, r
