@@ -1584,7 +1584,7 @@ extern "C" int frxStripMigrate(frWorld **ws, int n) {
     for (int k = 0; k < n; ++k) {
         frWorld *w = ws[k];
         cudaSetDevice(w->device);
-        fx_world_pull(w);
+        fx_world_pull_some(w, FX_DIRTY_POSROT);          // the positions decide; the rest follows only if somebody leaves
         const frWorld_::Strip &st = w->strip;
         const float h = 0.25f * st.margin;
         const bool has_left = st.peer[0] != nullptr || (st.nccl_comm && st.rank > 0);
@@ -1631,6 +1631,7 @@ extern "C" int frxStripMigrate(frWorld **ws, int n) {
         if (!st.nccl_comm) continue;
         cudaSetDevice(w->device);
         if (!mig_reserve(w)) return -1;
+        if (!out_left[(size_t) k].empty() || !out_right[(size_t) k].empty()) fx_world_pull(w);   // the emigrants' full rows
         cudaStream_t s = w->stream;
         const int left = st.rank - 1, right = st.rank + 1;
         std::vector<frBody *> sent[2];
