@@ -62,7 +62,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-sub", action="store_true", help="no config1/3/4/5 sub-records (profiling runs)")
     ap.add_argument("--sub-steps", type=int, default=200, help="timed steps of the config4 / config5 sub-records")
-    ap.add_argument("--sub-timeout", type=int, default=420, help="seconds after which the sub-records are abandoned and the line printed without them")
+    ap.add_argument("--sub-timeout", type=int, default=300, help="seconds after which the sub-records are abandoned and the line printed without them")
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"],
                     help="config2 (default, the headline): one 65,536-body mixed pile per GPU; config3: one 1M-circle column "
                          "collapse per GPU; config4: 4,096 independent 256-body worlds batched into one launch set and "

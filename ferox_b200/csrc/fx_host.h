@@ -150,6 +150,7 @@ struct frWorld_ {
         float cut_lo = 0.f, cut_hi = 0.f, margin = 0.f;
         unsigned int ghost_cap = 0;                  // ghost rows per side
         unsigned int uid_base = 0, uid_space = 0;    // this rank's slice of the global uid space
+        unsigned int uid_slice = 0;                  // ids this strip may hand out (0: up to the end of the space)
         unsigned char *send_full = nullptr;          // my left-border bodies  -> left neighbour
         unsigned char *recv_full = nullptr;          // right neighbour's left-border bodies = my ghosts
         float4 *send_vel = nullptr, *recv_vel = nullptr;       // border velocities: -> left / <- right

@@ -230,7 +230,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-// waits until the flag(s) have reached their epochs.  A lost neighbour must not hang the GPU: after 30 s the waiter gives
+// waits until the flag(s) have reached their epochs.  A lost neighbour must not hang the GPU: after 10 s the waiter gives
 // up, reports it (overflow bit 64) and latches `*dead`, which makes every later wait of this strip return at once.
 __global__ void k_strip_wait(DevWorld w, const unsigned int *flag_a, unsigned int epoch_a, const unsigned int *flag_b, unsigned int epoch_b,
                              unsigned int *dead) {
@@ -243,7 +243,7 @@ __global__ void k_strip_wait(DevWorld w, const unsigned int *flag_a, unsigned in
         const bool b = flag_b == nullptr || (int) (ld_acquire_sys(flag_b) - epoch_b) >= 0;
         if (a && b) return;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        if (t1 - t0 > 30000000000ull) { *dead = 1u; atomicOr(&w.ctr->overflow, 64u); return; }
+        if (t1 - t0 > 10000000000ull) { *dead = 1u; atomicOr(&w.ctr->overflow, 64u); return; }
     }
 }
 

@@ -541,6 +541,14 @@ static bool sync_shapes(frWorld *w) {
 }
 
 // ---- membership ----
+// a strip hands out ids from its own slice of the global id space only: ids are contact-cache keys and ghost rows carry
+// them across ranks, so two bodies must never share one
+static bool strip_uid_available(const frWorld *w) {
+    if (!w->strip.enabled || !w->uid_free.empty()) return true;
+    const unsigned long long limit = w->strip.uid_slice ? w->strip.uid_slice
+                                                         : (w->strip.uid_space > w->strip.uid_base ? w->strip.uid_space - w->strip.uid_base : 0u);
+    return (unsigned long long) w->uid_index.size() < limit;
+}
 static void attach_body(frWorld *w, frBody *b) {
     fx_world_pull(w);
     const int i = (int) w->bodies.size();
@@ -595,6 +603,7 @@ static void drain_queue(frWorld *w) {
         w->ring_tail = (w->ring_tail + 1) & mask;
         if (op.id == FX_OP_ADD) {
             if (op.body->world != nullptr) continue;   // duplicate adds / foreign bodies are not supported
+            if (!strip_uid_available(w)) { fx_set_error(8, "strip id slice exhausted: configure a larger uidSpace"); continue; }
             attach_body(w, op.body);
         } else if (op.id == FX_OP_REMOVE) {
             if (op.body->world == w) detach_body(w, op.body);
@@ -1262,6 +1271,7 @@ extern "C" int frxStripLinkLocal(frWorld *left, frWorld *right) {
     if (!left || !right || !left->strip.enabled || !right->strip.enabled || left->strip.ghost_cap != right->strip.ghost_cap) return -1;
     left->strip.peer[1] = right;
     right->strip.peer[0] = left;
+    if (right->strip.uid_base > left->strip.uid_base) left->strip.uid_slice = right->strip.uid_base - left->strip.uid_base;
     if (left->device != right->device) {
         int can = 0;
         cudaDeviceCanAccessPeer(&can, left->device, right->device);
@@ -1345,6 +1355,7 @@ extern "C" int frxStripInitNccl(frWorld *w, int rank, int nranks, const void *un
     w->strip.rank = rank;
     w->strip.nranks = nranks;
     if (!nccl_ok(g_nccl.CommInitRank(&w->strip.nccl_comm, nranks, id, rank), "ncclCommInitRank")) return -1;
+    if (nranks > 0) w->strip.uid_slice = w->strip.uid_space / (unsigned int) nranks;     // equal slices, rank r starts at r * slice
     strip_map_neighbour_inboxes(w);
     return 0;
 }
@@ -1543,6 +1554,11 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
         w->snapshot_pending = true;
         w->steps++;
         fx_cuda_ok(cudaGetLastError(), "strip step launch");
+        if (!w->uid_pending_free.empty()) {
+            // ids freed before this step are recyclable now: their cache entries were dropped by it
+            w->uid_free.insert(w->uid_free.end(), w->uid_pending_free.begin(), w->uid_pending_free.end());
+            w->uid_pending_free.clear();
+        }
         if (w->ring_head != w->ring_tail) drain_queue(w);
     }
 }
@@ -1606,6 +1622,7 @@ extern "C" int frxStripMigrate(frWorld **ws, int n) {
             std::vector<frBody *> &list = side == 0 ? out_left[(size_t) k] : out_right[(size_t) k];
             for (frBody *b : list) {
                 if ((int) p->bodies.size() >= p->capacity) p->capacity = (int) p->bodies.size() + 1;   // a move inside one world, not an add
+                if (!strip_uid_available(p)) { fx_set_error(8, "strip id slice exhausted: configure a larger uidSpace"); break; }
                 // every strip registered the same shape list in the same order (frxStripRegisterShapes): the body takes
                 // the neighbour's copy of its shape, so that shape-table indices keep meaning the same thing everywhere
                 auto it = w->shape_index.find(b->shape);
@@ -1699,6 +1716,7 @@ extern "C" int frxStripMigrate(frWorld **ws, int n) {
                 b->loc.aabb = m.aabb;
                 b->loc.force = m.force;
                 if ((int) w->bodies.size() >= w->capacity) w->capacity = (int) w->bodies.size() + 1;       // a move inside one world, not an add
+                if (!strip_uid_available(w)) { fx_set_error(8, "strip id slice exhausted: configure a larger uidSpace (an immigrant was dropped)"); std::free(b); continue; }
                 attach_body(w, b);
                 w->h.force[b->index] = m.force;
                 ++st.migrated_in;

@@ -537,9 +537,9 @@ class StripScene:
         self.lib, self.spec, self.n_strips, self.local = lib, spec, n_strips, [k]
         if device is not None:
             lib.frxSetDevice(device)
-        stride = spec.n + 64
+        stride = 2 * spec.n + 64          # id slice of a strip: room for as many immigrants (frxStripMigrate) as it has bodies
         w = lib.frCreateWorld(capi.Vector2(*spec.gravity), spec.cell)
-        lib.frxSetWorldCapacity(w, spec.n + 16)
+        lib.frxSetWorldCapacity(w, 2 * spec.n + 16)
         assert lib.frxStripConfigure(w, cut_lo, cut_hi, margin, ghost_cap, k * stride, n_strips * stride) == 0
         shapes = [make_shape(lib, s) for s in spec.shapes]
         arr = (C.c_void_p * len(shapes))(*shapes)
