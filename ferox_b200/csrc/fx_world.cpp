@@ -1223,7 +1223,7 @@ extern "C" int frxStripConfigure(frWorld *w, float cutLo, float cutHi, float mar
     st.uid_base = uidBase; st.uid_space = uidSpace;
     bool ok = fx_cuda_ok(cudaMalloc((void **) &st.send_full, full_bytes(w)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.inbox, inbox_bytes(w)), "cudaMalloc strip") &&
-              fx_cuda_ok(cudaMalloc((void **) &st.push_done, 4 * sizeof(unsigned int)), "cudaMalloc strip") &&
+              fx_cuda_ok(cudaMalloc((void **) &st.push_done, 8 * sizeof(unsigned int)), "cudaMalloc strip") &&   // [0..3] counters, [4..7] an empty message header
               fx_cuda_ok(cudaMalloc((void **) &st.send_vel, vel_bytes(w)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.send_delta, vel_bytes(w)), "cudaMalloc strip") &&
               fx_cuda_ok(cudaMalloc((void **) &st.ghost_before, vel_bytes(w)), "cudaMalloc strip") &&
@@ -1242,7 +1242,7 @@ extern "C" int frxStripConfigure(frWorld *w, float cutLo, float cutHi, float mar
         st.recv_delta = st.recv_delta_buf[0];
         cudaMemsetAsync(st.send_full, 0, full_bytes(w), w->stream);
         cudaMemsetAsync(st.inbox, 0, inbox_bytes(w), w->stream);        // flags 0, ghost count 0 until a neighbour writes
-        cudaMemsetAsync(st.push_done, 0, 4 * sizeof(unsigned int), w->stream);
+        cudaMemsetAsync(st.push_done, 0, 8 * sizeof(unsigned int), w->stream);
         cudaMemsetAsync(st.send_vel, 0, vel_bytes(w), w->stream);
         cudaMemsetAsync(st.send_delta, 0, vel_bytes(w), w->stream);
         cudaMemsetAsync(st.ghost_cnt, 0, sizeof(unsigned int), w->stream);
@@ -1463,9 +1463,10 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
         world_push(w);
         fill_dev_params(w, dt);
         if (!st.ghosts_primed) {
-            // make every ghost row inert once (and after every rebuild of the uid map)
-            cudaMemsetAsync(st.recv_full, 0, FX_MSG_HEADER, w->stream);
-            fx_launch_strip_unpack(w->dw, w->cx, st.recv_full, w->dw.n_owned, st.ghost_cap, st.ghost_cnt);
+            // make every ghost row inert once (and after every rebuild of the uid map): unpack an EMPTY message.  (Not the
+            // receive buffer with its count cleared: with the peer-direct transport the right neighbour may already have
+            // stored this step's rows there.)
+            fx_launch_strip_unpack(w->dw, w->cx, reinterpret_cast<const unsigned char *>(st.push_done + 4), w->dw.n_owned, st.ghost_cap, st.ghost_cnt);
             st.ghosts_primed = true;
         }
         // (nothing has been exchanged yet: a failure here leaves no neighbour waiting inside a send/recv group)
