@@ -880,17 +880,24 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
         transport = {0: "in-process", 1: "NCCL send/recv", 2: "peer-direct (stores into the neighbour's IPC-mapped inbox over NVLink + flags; "
                      "NCCL for set-up and migration)"}.get(L.frxStripGetTransport(sc.world), "?")
         every = 100                                  # ownership migration period (steps), inside the timed region as well
-        moved = 0
+        moved, mig_s, mig_calls = 0, 0.0, 0
 
         def run(k):
-            nonlocal moved
+            nonlocal moved, mig_s, mig_calls
             done = 0
             while done < k:
                 chunk = min(every, k - done)
                 sc.step(chunk)
                 done += chunk
                 if chunk == every:
+                    L.frxSynchronizeWorld(sc.world)
+                    t0 = time.perf_counter()
                     moved += max(0, L.frxStripMigrate(sc._arr, 1))
+                    sc.step(1)                       # the step after a migration re-uploads and re-sizes: part of its cost
+                    L.frxSynchronizeWorld(sc.world)
+                    mig_s += time.perf_counter() - t0
+                    mig_calls += 1
+                    done += 1
         run(600)
         L.frxSynchronizeWorld(sc.world)
         sc.step(3)
@@ -918,7 +925,9 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
                 "n_gpus": world_size, "nccl_ranks": world_size, "transport": transport, "bodies_total": int(total), "steps": steps, "ms_per_step": elapsed / steps,
                 "hz": 1e3 * steps / elapsed, "value": total * steps / (elapsed * 1e-3), "unit": UNIT, "counters_rank0": ctr,
                 "overflow_max_over_ranks": int(over), "error_rank0": err, "migration_every_steps": every,
-                "migrated_bodies_all_ranks": int(reduce_sum(moved))}
+                "migrated_bodies_all_ranks": int(reduce_sum(moved)),
+                "migration_ms_per_call_rank0": 1e3 * mig_s / max(1, mig_calls),
+                "migration_note": "wall clock of frxStripMigrate + the step that follows it (re-upload, re-sizing) on rank 0, minus nothing"}
     out["config5"] = guarded("config5", c5_multi)
     return out
 

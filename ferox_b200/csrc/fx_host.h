@@ -119,6 +119,7 @@ struct frWorld_ {
     ShapeDev *d_shapes = nullptr;
     int d_shapes_cap = 0;
     uint64_t shape_epoch_seen = 0;
+    bool shape_rows_stale = false;   // a member body changed its shape: every row's table index is looked up again (adds / removes keep their own rows)
 
     // uid allocator
     std::vector<int> uid_index;          // uid -> world index or -1
