@@ -362,6 +362,7 @@ void fx_world_mark_body(frWorld *w, int index, unsigned bits) {
         const StepCountersDev &c = w->last;
         if (x0 >= c.cell_min_x && y0 >= c.cell_min_y && x1 <= c.cell_max_x && y1 <= c.cell_max_y) {
             w->dirty |= bits;
+            if (bits & FX_DIRTY_SHAPE) w->shape_rows_stale = true;
             return;
         }
     }
