@@ -879,7 +879,7 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
         sc, spec = build_config5_strip(L, 1048576, rank, world_size, local_rank, dist, args.margin, args.ghost_cap)
         transport = {0: "in-process", 1: "NCCL send/recv", 2: "peer-direct (stores into the neighbour's IPC-mapped inbox over NVLink + flags; "
                      "NCCL for set-up and migration)"}.get(L.frxStripGetTransport(sc.world), "?")
-        every = 100                                  # ownership migration period (steps), inside the timed region as well
+        every = 200                                  # ownership migration period (steps), inside the timed region as well
         moved, mig_s, mig_calls = 0, 0.0, 0
 
         def run(k):
@@ -919,7 +919,7 @@ def run_sub_records(L, args, rank, world_size, local_rank, dist, barrier):
         sc.release()
         return {"workload": "config5: ONE pile of %d x 1,048,576 mixed bodies on 8 storeys cut into %d vertical strips, one per GPU; ghost "
                             "rows (96 B) once per step and 16-byte velocity changes after each of the 11 solver stages exchanged between "
-                            "neighbours (transport: see `transport`); ownership migration (frxStripMigrate) every 100 "
+                            "neighbours (transport: see `transport`); ownership migration (frxStripMigrate) every 200 "
                             "steps, also inside the timed region; settled 600 steps; one event bracket "
                             "around %d steps, MAX over ranks (per-step working set > 2 GB per GPU)" % (world_size, world_size, steps),
                 "n_gpus": world_size, "nccl_ranks": world_size, "transport": transport, "bodies_total": int(total), "steps": steps, "ms_per_step": elapsed / steps,
