@@ -1611,12 +1611,17 @@ extern "C" int frxStripMigrate(frWorld **ws, int n) {
         const float h = 0.25f * st.margin;
         const bool has_left = st.peer[0] != nullptr || (st.nccl_comm && st.rank > 0);
         const bool has_right = st.peer[1] != nullptr || (st.nccl_comm && st.rank + 1 < st.nranks);
-        for (size_t i = 0; i < w->bodies.size(); ++i) {
-            frBody *b = w->bodies[i];
-            if (b->type == FR_BODY_STATIC) continue;           // static bodies are replicated, never exchanged
-            const float px = w->h.posrot[i].x;
-            if (has_left && px < st.cut_lo - h) out_left[(size_t) k].push_back(b);
-            else if (has_right && px >= st.cut_hi + h) out_right[(size_t) k].push_back(b);
+        // (the scan reads the packed mirror only -- positions and the type bits -- not a million body objects)
+        const float4 *posrot = w->h.posrot, *mprop = w->h.mprop;
+        const float lo = st.cut_lo - h, hi = st.cut_hi + h;
+        for (size_t i = 0, nb = w->bodies.size(); i < nb; ++i) {
+            const float px = posrot[i].x;
+            if (!((has_left && px < lo) || (has_right && px >= hi))) continue;
+            uint32_t bits;
+            std::memcpy(&bits, &mprop[i].w, sizeof bits);
+            if ((bits & 0xffu) == (uint32_t) FR_BODY_STATIC) continue;   // static bodies are replicated, never exchanged
+            if (has_left && px < lo) out_left[(size_t) k].push_back(w->bodies[i]);
+            else out_right[(size_t) k].push_back(w->bodies[i]);
         }
     }
     // ---- in-process neighbours: the body itself changes world
