@@ -83,11 +83,12 @@ struct ManifoldSet {
 // by every Gauss-Seidel sweep.
 struct SolverSet {
     int2 *body;      // {idxA, idxB}
-    float4 *nt;      // {n.x, n.y, t.x, t.y}
+    float4 *nt;      // {n.x, n.y, t.x, t.y}                            (full records)
+    float2 *n;       // contact normal; the tangent is recomputed from it   (lean records, fx_solve.cu load_nt)
     float4 *mat;     // {friction, restitution, invInertiaA, invInertiaB}
     int *count_src;  // count | (source manifold index << 2)
     float4 *r;       // [2][cap] contact-major: {r1.x, r1.y, r2.x, r2.y}
-    float4 *u;       // [2][cap] {u1.x, u1.y, u2.x, u2.y}   unit left-normals of r1, r2
+    float4 *u;       // [2][cap] {u1.x, u1.y, u2.x, u2.y}   unit left-normals of r1, r2   (full records only)
     float4 *k;       // [2][cap] {bias, normalMass, tangentMass, 0}
     float2 *lam;     // [2][cap] {normalScalar, tangentScalar}
 };
@@ -169,6 +170,7 @@ struct DevWorld {
     unsigned int *h_slot;                // [cap_hash] index into the dense array the table was built over, ~0u: empty
     // solver
     SolverSet sol;
+    int sol_lean;        // solver records without what a sweep can recompute (see SolverSet)
     unsigned int sol_stride, sol_mult;   // per-contact record (slot s, contact c) lives at c * sol_stride + s * sol_mult
     unsigned int *order;                 // manifold indices grouped by colour
     unsigned int *color_off;             // [FX_MAX_COLORS + 1]

@@ -87,6 +87,7 @@ struct WarmRec {
 };
 
 // build the solver record of manifold m at slot s: everything that depends on positions only (src/rigid_body.c:350-385)
+template <bool LEAN>
 __device__ __forceinline__ WarmRec build_record(const DevWorld &w, const ManifoldSet &man, unsigned int m, unsigned int s, float inv_ma,
                                                 float inv_mb, float inv_dt) {
     WarmRec q;
@@ -111,7 +112,8 @@ __device__ __forceinline__ WarmRec build_record(const DevWorld &w, const Manifol
     q.r[0] = q.r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
     q.lam[0] = q.lam[1] = make_float2(0.f, 0.f);
     w.sol.body[s] = b;
-    w.sol.nt[s] = q.nt;
+    if (LEAN) w.sol.n[s] = make_float2(n.x, n.y);
+    else w.sol.nt[s] = q.nt;
     w.sol.mat[s] = q.mat;
     w.sol.count_src[s] = cs;
     if (!active) return q;
@@ -127,18 +129,34 @@ __device__ __forceinline__ WarmRec build_record(const DevWorld &w, const Manifol
         q.r[c] = make_float4(k.r1.x, k.r1.y, k.r2.x, k.r2.y);
         q.lam[c] = make_float2(im.y, im.w);
         w.sol.r[SOL_AT(w, s, c)] = q.r[c];
-        w.sol.u[SOL_AT(w, s, c)] = make_float4(k.u1.x, k.u1.y, k.u2.x, k.u2.y);
+        if (!LEAN) w.sol.u[SOL_AT(w, s, c)] = make_float4(k.u1.x, k.u1.y, k.u2.x, k.u2.y);
         w.sol.k[SOL_AT(w, s, c)] = make_float4(k.bias, k.nmass, k.tmass, 0.0f);
         w.sol.lam[SOL_AT(w, s, c)] = q.lam[c];
     }
     return q;
 }
 
+// LEAN records (w.sol_lean: large worlds swept by k_solve_colored, whose sweeps stream the records from DRAM): a
+// record keeps only what cannot be recomputed bit for bit from the rest of it -- the normal (the tangent is
+// frVector2RightNormal of it, as in build_record) and the lever arms (the unit perpendiculars `u` of the relative
+// velocity's angular term are frVector2LeftNormal of them, contact_arms) -- and a sweep reads 76 bytes per manifold
+// instead of 100 (40 instead of 56 for a second contact).  [measured] 1 M circles: solve 1.83 -> 1.72 ms.  Small and
+// batched worlds keep the full records: their phases are latency-bound and the square roots sit on the critical path
+// ([measured] with lean records: config 2 solve 0.294 -> 0.305 ms, config 4 0.96 -> 1.13 ms).
+template <bool LEAN>
+__device__ __forceinline__ float4 load_nt(const DevWorld &w, unsigned int s) {
+    if (!LEAN) return w.sol.nt[s];
+    const float2 n = w.sol.n[s];
+    const V2 t = vperp_right(v2(n.x, n.y));
+    return make_float4(n.x, n.y, t.x, t.y);
+}
+
+template <bool LEAN>
 __device__ __forceinline__ WarmRec load_warm_record(const DevWorld &w, unsigned int s, int2 b, int cs) {
     WarmRec q;
     q.b = b;
     q.cs = cs;
-    q.nt = w.sol.nt[s];
+    q.nt = load_nt<LEAN>(w, s);
     q.mat = w.sol.mat[s];
     const int count = CS_COUNT(cs);
     q.r[0] = q.r[1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -176,35 +194,37 @@ __device__ __forceinline__ void warm_start_apply(const WarmRec &q, const Vel &ve
     if (inv_mb > 0.0f || inv_ib > 0.0f) vel.store(q.b.y, make_float4(vb.x, vb.y, vb.w, inv_mb));
 }
 
-template <class Vel>
+template <bool LEAN, class Vel>
 __device__ __forceinline__ void prepare_and_warm_start(const DevWorld &w, const ManifoldSet &man, unsigned int m, unsigned int s,
                                                        const Vel &vel, float inv_dt) {
     const int2 b = man.body[m];
-    warm_start_apply(build_record(w, man, m, s, vel.load(b.x).w, vel.load(b.y).w, inv_dt), vel);
+    warm_start_apply(build_record<LEAN>(w, man, m, s, vel.load(b.x).w, vel.load(b.y).w, inv_dt), vel);
 }
 
 // what a sweep reads of a slot through the slot index alone ("level 1"); it does not depend on any velocity
 struct SweepRec {
     int cs;
     int2 b;
-    float4 nt, mat, r0, u0, k0;
+    float4 nt, mat, r0, u0, k0;      // (u0: full records only)
     float2 l0;
 };
+template <bool LEAN>
 __device__ __forceinline__ SweepRec sweep_load_rest(const DevWorld &w, unsigned int s, int2 b, int cs) {
     SweepRec q;
     q.cs = cs;
     q.b = b;
-    q.nt = w.sol.nt[s];
+    q.nt = load_nt<LEAN>(w, s);
     q.mat = w.sol.mat[s];
-    q.r0 = w.sol.r[SOL_AT(w, s, 0)]; q.u0 = w.sol.u[SOL_AT(w, s, 0)]; q.k0 = w.sol.k[SOL_AT(w, s, 0)];
+    q.r0 = w.sol.r[SOL_AT(w, s, 0)]; q.u0 = LEAN ? q.r0 : w.sol.u[SOL_AT(w, s, 0)]; q.k0 = w.sol.k[SOL_AT(w, s, 0)];
     q.l0 = w.sol.lam[SOL_AT(w, s, 0)];
     return q;
 }
+template <bool LEAN>
 __device__ __forceinline__ SweepRec sweep_load(const DevWorld &w, unsigned int s) {
-    return sweep_load_rest(w, s, w.sol.body[s], w.sol.count_src[s]);
+    return sweep_load_rest<LEAN>(w, s, w.sol.body[s], w.sol.count_src[s]);
 }
 // one Gauss-Seidel update of the manifold at slot s; va4 / vb4: the velocities of its bodies as just loaded
-template <class Vel>
+template <bool LEAN, class Vel>
 __device__ __forceinline__ void sweep_apply(const DevWorld &w, unsigned int s, const SweepRec &q, float4 va4, float4 vb4, const Vel &vel) {
     const int count = CS_COUNT(q.cs);
     // level 2: the velocities (addressed through b) and, for the few two-contact manifolds, the second record
@@ -212,19 +232,23 @@ __device__ __forceinline__ void sweep_apply(const DevWorld &w, unsigned int s, c
     float4 r1 = q.r0, u1 = q.u0, k1 = q.k0;
     float2 l0 = q.l0, l1 = q.l0;
     if (count > 1) {
-        r1 = w.sol.r[SOL_AT(w, s, 1)]; u1 = w.sol.u[SOL_AT(w, s, 1)]; k1 = w.sol.k[SOL_AT(w, s, 1)];
+        r1 = w.sol.r[SOL_AT(w, s, 1)];
+        if (!LEAN) u1 = w.sol.u[SOL_AT(w, s, 1)];
+        k1 = w.sol.k[SOL_AT(w, s, 1)];
         l1 = w.sol.lam[SOL_AT(w, s, 1)];
     }
     Vel3 va = { va4.x, va4.y, va4.z }, vb = { vb4.x, vb4.y, vb4.z };
     const V2 n = v2(q.nt.x, q.nt.y), t = v2(q.nt.z, q.nt.w);
     ContactK k;
     k.r1 = v2(q.r0.x, q.r0.y); k.r2 = v2(q.r0.z, q.r0.w);
-    k.u1 = v2(q.u0.x, q.u0.y); k.u2 = v2(q.u0.z, q.u0.w);
+    if (LEAN) { k.u1 = vperp_left(k.r1); k.u2 = vperp_left(k.r2); }
+    else { k.u1 = v2(q.u0.x, q.u0.y); k.u2 = v2(q.u0.z, q.u0.w); }
     k.bias = q.k0.x; k.nmass = q.k0.y; k.tmass = q.k0.z;
     contact_resolve(k, n, t, q.mat.x, q.mat.y, l0.x, l0.y, va4.w, vb4.w, q.mat.z, q.mat.w, va, vb);
     if (count > 1) {
         k.r1 = v2(r1.x, r1.y); k.r2 = v2(r1.z, r1.w);
-        k.u1 = v2(u1.x, u1.y); k.u2 = v2(u1.z, u1.w);
+        if (LEAN) { k.u1 = vperp_left(k.r1); k.u2 = vperp_left(k.r2); }
+        else { k.u1 = v2(u1.x, u1.y); k.u2 = v2(u1.z, u1.w); }
         k.bias = k1.x; k.nmass = k1.y; k.tmass = k1.z;
         contact_resolve(k, n, t, q.mat.x, q.mat.y, l1.x, l1.y, va4.w, vb4.w, q.mat.z, q.mat.w, va, vb);
     }
@@ -233,11 +257,11 @@ __device__ __forceinline__ void sweep_apply(const DevWorld &w, unsigned int s, c
     w.sol.lam[SOL_AT(w, s, 0)] = l0;
     if (count > 1) w.sol.lam[SOL_AT(w, s, 1)] = l1;
 }
-template <class Vel>
+template <bool LEAN, class Vel>
 __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, const Vel &vel) {
-    const SweepRec q = sweep_load(w, s);
+    const SweepRec q = sweep_load<LEAN>(w, s);
     if (CS_COUNT(q.cs) == 0) return;
-    sweep_apply(w, s, q, vel.load(q.b.x), vel.load(q.b.y), vel);
+    sweep_apply<LEAN>(w, s, q, vel.load(q.b.x), vel.load(q.b.y), vel);
 }
 
 // `phases`: bit 0 = colouring + ordering + solver records + warm start, bit 1 = `iterations` sweeps,
@@ -250,7 +274,8 @@ __device__ __forceinline__ void sweep_one(const DevWorld &w, unsigned int s, con
 // Two builds of the same kernel: MINB = 1 may use 128 registers (96 used, no spills; one block per SM: the
 // latency-bound small-world case), MINB = 2 is held to 64 registers so that two blocks fit an SM (large worlds
 // want the threads).  [measured] solve at 65k bodies 0.323 (MINB 1) vs 0.330 ms; at 1 M bodies 2.46 vs 2.27 ms.
-template <int MINB>
+// LEAN: the records hold the normal and the lever arms only (load_nt above); the host picks the build from w.sol_lean.
+template <int MINB, bool LEAN>
 __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, int iterations, int phases) {
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned int s_hist[FX_MAX_COLORS];
@@ -409,14 +434,14 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
         for (unsigned int s = tid; s < M; s += nth) {
             const unsigned int m = w.order[s];
             const int2 b = man.body[m];
-            build_record(w, man, m, s, w.vel[b.x].w, w.vel[b.y].w, inv_dt);
+            build_record<LEAN>(w, man, m, s, w.vel[b.x].w, w.vel[b.y].w, inv_dt);
         }
         return;
     }
     // ---- phase 3: solver records + warm start, one colour at a time
     for (unsigned int c = 0; c < s_ncolors; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
-        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, gvel, inv_dt);
+        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start<LEAN>(w, man, w.order[s], s, gvel, inv_dt);
         grid.sync();
     }
     } else {
@@ -433,6 +458,10 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     // ([measured] sweeping the sparse trailing colours -- config 2: 25371, 23942, 22512, 20101, 16451, 10719, 1263, 33 manifolds
     // per colour -- by block 0 alone behind ONE grid barrier was bit-identical and slower, solve 0.296 -> 0.343 ms: three
     // block-serial rounds of dependent L2 round trips cost more than the barrier they save)
+    // ([measured] asking L2 for the NEXT phase's records -- prefetch.global.L2 on the very slots a thread sweeps next, issued at
+    // the start of a phase so that DRAM keeps streaming under the gather, the arithmetic and the barrier -- at 1 M bodies,
+    // where a colour's records are ~40 MB and come from DRAM in every sweep: bit-identical, solve 1.837 -> 2.003 ms.  Nothing
+    // is saturated there (DRAM 31 %, L2 34 %); two colours' records do not stay in L2 next to the velocities)
     // ([measured] fetching a thread's NEXT record between the halves of a split grid barrier -- grid.barrier_arrive(), loads,
     // grid.barrier_wait() -- was bit-identical and no faster either, solve 0.297 -> 0.309 ms at 65k bodies: the phase is
     // bound by the barrier and the velocity gather that can only start behind it, not by the record fetch)
@@ -440,7 +469,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     for (int it = 0; it < iterations; ++it)
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
-            for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one(w, s, gvel2);
+            for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one<LEAN>(w, s, gvel2);
             grid.sync();
         }
     // ---- phase 5: write the impulses and effective masses back to the cache
@@ -614,13 +643,13 @@ __global__ void __launch_bounds__(1024, 1) k_solve_local(DevWorld w, int iterati
         const VelArray lvel = { svel, lo };
         for (unsigned int c = 0; c < ncolors; ++c) {
             if (s_off[c] == s_off[c + 1]) continue;
-            for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) prepare_and_warm_start(w, man, w.order[s], s, lvel, inv_dt);
+            for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) prepare_and_warm_start<false>(w, man, w.order[s], s, lvel, inv_dt);
             __syncthreads();
         }
         for (int it = 0; it < iterations; ++it)
             for (unsigned int c = 0; c < ncolors; ++c) {
                 if (s_off[c] == s_off[c + 1]) continue;
-                for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) sweep_one(w, s, lvel);
+                for (unsigned int s = mbase + s_off[c] + tid; s < mbase + s_off[c + 1]; s += nth) sweep_one<false>(w, s, lvel);
                 __syncthreads();
             }
         for (unsigned int s = mbase + tid; s < mbase + mc; s += nth) {
@@ -1050,12 +1079,12 @@ __global__ void __launch_bounds__(CL_BLOCK, 1) k_sweep_cluster(DevWorld w, int i
                 ++consumed;
                 if (!valid) continue;
                 if (it < 0) {
-                    warm_start_apply(load_warm_record(w, s, body, cs), vel);
+                    warm_start_apply(load_warm_record<false>(w, s, body, cs), vel);
                 } else if (CS_COUNT(cs) != 0) {
                     float4 *pa = vel.at(body.x), *pb = vel.at(body.y);
                     const float4 va4 = *pa, vb4 = *pb;            // DSMEM gathers in flight while the record streams in from L2
-                    const SweepRec q = sweep_load_rest(w, s, body, cs);
-                    sweep_apply(w, s, q, va4, vb4, vel);
+                    const SweepRec q = sweep_load_rest<false>(w, s, body, cs);
+                    sweep_apply<false>(w, s, q, va4, vb4, vel);
                 }
             }
             cluster.sync();
@@ -1136,7 +1165,7 @@ void fx_launch_solve_cluster(const DevWorld &w, const FxLaunchCtx &cx, int itera
 int fx_query_coop_blocks(int device) {
     int sms = 0, per_sm = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_colored<2>, SV_BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve_colored<2, false>, SV_BLOCK, 0);
     if (per_sm > 4) per_sm = 4;
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;
@@ -1168,7 +1197,8 @@ void fx_launch_solve_colored(const DevWorld &w, const FxLaunchCtx &cx, int itera
     const int blocks = fx_solve_colored_blocks(cx, work_hint);
     DevWorld wc = w;
     void *args[] = { (void *) &wc, (void *) &iterations, (void *) &phases };
-    const void *kernel = solve_wide(work_hint) ? (const void *) k_solve_colored<2> : (const void *) k_solve_colored<1>;
+    const void *kernel = solve_wide(work_hint) ? (w.sol_lean ? (const void *) k_solve_colored<2, true> : (const void *) k_solve_colored<2, false>)
+                                               : (w.sol_lean ? (const void *) k_solve_colored<1, true> : (const void *) k_solve_colored<1, false>);
     cudaLaunchCooperativeKernel(kernel, dim3(blocks), dim3(SV_BLOCK), args, 0, cx.stream);
     ++g_fx_launches;
 }

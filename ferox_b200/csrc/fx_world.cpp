@@ -180,7 +180,7 @@ static void world_free_device(frWorld *w) {
     cudaFree(d.cand); cudaFree(d.cand_hit);
     free_manifold_set(d.man[0]); free_manifold_set(d.man[1]);
     cudaFree(d.touched); cudaFree(d.h_slot);
-    cudaFree(d.sol.body); cudaFree(d.sol.nt); cudaFree(d.sol.mat); cudaFree(d.sol.count_src);
+    cudaFree(d.sol.body); cudaFree(d.sol.nt); cudaFree(d.sol.n); cudaFree(d.sol.mat); cudaFree(d.sol.count_src);
     cudaFree(d.sol.r); cudaFree(d.sol.u); cudaFree(d.sol.k); cudaFree(d.sol.lam);
     cudaFree(d.order); cudaFree(d.color_off); cudaFree(d.body_mask); cudaFree(d.body_dup); cudaFree(d.winner); cudaFree(d.cbody);
     cudaFree(d.color_scratch); cudaFree(d.ctr); cudaFree(d.prev_count); cudaFree(d.cur_flip); cudaFree(w->d_scal);
@@ -674,7 +674,7 @@ static bool ensure_work_capacity(frWorld *w, unsigned long long ent, unsigned lo
         ok = ok && dev_realloc(d.touched, 0, cap, s, false) && dev_realloc(d.cbody, 0, cap, s, false) &&
              dev_realloc(d.order, 0, cap, s, false);
         // (+ 8: the cluster solver's bulk copies round their end up to 16 bytes)
-        ok = ok && dev_realloc(d.sol.body, 0, (size_t) cap + 8, s, false) && dev_realloc(d.sol.nt, 0, cap, s, false) &&
+        ok = ok && dev_realloc(d.sol.body, 0, (size_t) cap + 8, s, false) && dev_realloc(d.sol.nt, 0, cap, s, false) && dev_realloc(d.sol.n, 0, cap, s, false) &&
              dev_realloc(d.sol.mat, 0, cap, s, false) && dev_realloc(d.sol.count_src, 0, (size_t) cap + 8, s, false) &&
              dev_realloc(d.sol.r, 0, 2 * (size_t) cap, s, false) && dev_realloc(d.sol.u, 0, 2 * (size_t) cap, s, false) &&
              dev_realloc(d.sol.k, 0, 2 * (size_t) cap, s, false) && dev_realloc(d.sol.lam, 0, 2 * (size_t) cap, s, false);
@@ -769,6 +769,9 @@ static void fill_dev_params(frWorld *w, float dt) {
         const bool contact_major = w->force_large || w->manifold_hint >= 400000;
         d.sol_stride = contact_major ? d.cap_manifolds : 1u;
         d.sol_mult = contact_major ? 1u : 2u;
+        // lean records where the sweeps are bandwidth-bound: large worlds that k_solve_colored takes (fx_solve.cu load_nt)
+        // (the block-local and the cluster solver read full records)
+        d.sol_lean = (contact_major && !(w->use_local && w->local_max_bodies > 0) && (w->force_large || fx_cluster_size_for(d.n) == 0)) ? 1 : 0;
     }
     {
         static const int narrow = [] { const char *e = std::getenv("FEROX_NARROWPHASE"); return !e ? 0 : (std::strcmp(e, "group8") == 0 ? 1 : (std::strcmp(e, "lane") == 0 ? 2 : 0)); }();
@@ -1535,7 +1538,6 @@ extern "C" void frxStripStep(frWorld **ws, int n, float dt) {
         for (int k = 0; k < n; ++k) {
             frWorld *w = ws[k];
             cudaSetDevice(w->device);
-            frWorld_::Strip &st = w->strip;
             const long long hint = w->manifold_hint > (long long) w->dw.n ? w->manifold_hint : (long long) w->dw.n;
             fx_launch_solve_colored(w->dw, w->cx, 1, hint, 2 /* one sweep */);      // "before" values: written by the last stage_apply
         }
