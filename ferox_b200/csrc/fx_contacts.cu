@@ -303,7 +303,7 @@ __device__ __forceinline__ void slot_store(NpSlot &s, const Manifold &m) {
 #define NP2_SMEM(ITEMS) ((size_t) NP2_BLOCK * (ITEMS) * (sizeof(NpSlot) + 2 * sizeof(unsigned short)))
 
 template <int NP2_ITEMS>
-__global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, unsigned long long *status, unsigned int *ticket) {
+__global__ void __launch_bounds__(NP2_BLOCK, NP2_ITEMS >= 4 ? 3 : 4) k_narrowphase_tiled(DevWorld w, unsigned long long *status, unsigned int *ticket) {
     constexpr unsigned int NP2_TILE = NP2_BLOCK * NP2_ITEMS;
     extern __shared__ __align__(16) unsigned char np_smem[];
     NpSlot *slot = reinterpret_cast<NpSlot *>(np_smem);
@@ -387,7 +387,13 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
             }
         }
         __syncthreads();
-        // ---- C: ordered compaction (candidate order), cache probe, write
+        // ---- C: ordered compaction (candidate order), cache probe, write.
+        // Every candidate -- hit or miss -- probes the previous step's cache (src/world.c:347-394), and a hit then reads
+        // its old entry: a chain of five dependent scattered loads (uid -> table slot -> key -> header / ids -> impulses).
+        // The chains of a thread's candidates are walked SIDE BY SIDE, one level at a time, with no store in between (a
+        // store would pin the later loads behind it), and the probe goes out before the block's look-back, which it does
+        // not depend on; [measured] one candidate after the other: 57 % of the kernel's stall samples sat here, on
+        // the long scoreboard at 13 active lanes per warp.
         unsigned int mine = 0u, q = 0u;
 #pragma unroll
         for (int j = 0; j < NP2_ITEMS; ++j) {
@@ -397,56 +403,108 @@ __global__ void __launch_bounds__(NP2_BLOCK) k_narrowphase_tiled(DevWorld w, uns
         }
         unsigned int total;
         const unsigned int excl = block_exclusive_scan<NP2_BLOCK>(mine, &total);
-        const unsigned int base = tile_exclusive_prefix(status, tile, total);
-        unsigned int pos = base + excl;
+        tile_publish_aggregate(status, tile, total);                // the tiles behind this one do not wait for its probes
+        // level 1: the uids of both bodies
+        unsigned int ua[NP2_ITEMS], ub[NP2_ITEMS];
+#pragma unroll
+        for (int j = 0; j < NP2_ITEMS; ++j) {
+            ua[j] = ub[j] = 0u;
+            if (pr[j].x >= 0) { ua[j] = w.uid[pr[j].x]; ub[j] = w.uid[pr[j].y]; }
+        }
+        // level 2: the first table slot of every probe; level 3: the key it points at
+        const unsigned int hmask = w.cap_hash - 1u;
+        unsigned int hv[NP2_ITEMS];
+#pragma unroll
+        for (int j = 0; j < NP2_ITEMS; ++j) {
+            hv[j] = 0xffffffffu;
+            if (pr[j].x >= 0) hv[j] = w.h_slot[hash_slot(((unsigned long long) ua[j] << 32) | (unsigned long long) ub[j], hmask)];
+        }
+        uint2 hk[NP2_ITEMS];
+#pragma unroll
+        for (int j = 0; j < NP2_ITEMS; ++j) {
+            hk[j] = make_uint2(0u, 0u);
+            if (hv[j] != 0xffffffffu) hk[j] = prev.key[hv[j]];
+        }
+        int old[NP2_ITEMS];
+#pragma unroll
+        for (int j = 0; j < NP2_ITEMS; ++j) {
+            old[j] = -1;
+            if (hv[j] == 0xffffffffu) continue;                     // empty slot: the pair has no entry
+            if (hk[j].x == ua[j] && hk[j].y == ub[j]) { old[j] = (int) hv[j]; continue; }
+            // the slot belongs to another pair: walk on from it (rare; hash_find restarts at the home slot)
+            old[j] = hash_find(w, ((unsigned long long) ua[j] << 32) | (unsigned long long) ub[j], prev.key);
+        }
 #pragma unroll
         for (int j = 0; j < NP2_ITEMS; ++j) {
             if (pr[j].x < 0) continue;
-            const unsigned int c = first + j;
-            const NpSlot &sl = slot[threadIdx.x * NP2_ITEMS + j];
-            const bool hit = sl.count > 0;
-            const unsigned int ua = w.uid[pr[j].x], ub = w.uid[pr[j].y];
-            const unsigned long long key = ((unsigned long long) ua << 32) | (unsigned long long) ub;
-            const int old = hash_find(w, key, prev.key);            // src/world.c:347-394
-            if (old >= 0) w.touched[old] = 1;
-            w.cand_hit[c] = hit ? 1 : 0;
-            if (!hit) continue;
-            float friction, restitution;
-            float lam_n0 = 0.0f, lam_t0 = 0.0f, lam_n1 = 0.0f, lam_t1 = 0.0f;
-            int color = -1;
-            if (old >= 0) {
-                const float4 oh = prev.hdr[old];
-                friction = oh.z;
-                restitution = oh.w;
-                const int2 ometa = prev.meta[old];
-                color = ometa.y;                                    // keep last step's colour
-                const int oid0 = prev.cid[2 * old], oid1 = prev.cid[2 * old + 1];
-                int o0 = -1, o1 = -1;
-                if (ometa.x > 0 && sl.id0 == oid0) o0 = 0; else if (ometa.x > 1 && sl.id0 == oid1) o0 = 1;
-                if (sl.count > 1) { if (ometa.x > 0 && sl.id1 == oid0) o1 = 0; else if (ometa.x > 1 && sl.id1 == oid1) o1 = 1; }
-                if (o0 >= 0) { const float4 oi = prev.imp[2 * old + o0]; lam_n0 = oi.y; lam_t0 = oi.w; }
-                if (o1 >= 0) { const float4 oi = prev.imp[2 * old + o1]; lam_n1 = oi.y; lam_t1 = oi.w; }
-            } else {                                                // new entry: src/world.c:395-404
-                const ShapeDev *s1 = &w.shapes[w.shape[pr[j].x].x], *s2 = &w.shapes[w.shape[pr[j].y].x];
-                friction = 0.5f * (s1->friction + s2->friction);
-                restitution = pin_fminf(s1->restitution, s2->restitution);
-                if (friction < 0.0f) friction = 0.0f;
-                if (restitution < 0.0f) restitution = 0.0f;
+            if (old[j] >= 0) w.touched[old[j]] = 1;
+            w.cand_hit[first + j] = slot[threadIdx.x * NP2_ITEMS + j].count > 0 ? 1 : 0;
+        }
+        const unsigned int base = tile_exclusive_prefix(status, tile, total);
+        unsigned int pos = base + excl;
+        // level 4: header, contact count / colour and feature ids of the old entries of this thread's hits -- two candidates at
+        // a time (four would not fit the 64 registers that keep four blocks on an SM)
+        constexpr int NP2_PAIR = NP2_ITEMS < 2 ? 1 : 2;
+#pragma unroll
+        for (int j0 = 0; j0 < NP2_ITEMS; j0 += NP2_PAIR) {
+            float4 oh[NP2_PAIR];
+            int2 ometa[NP2_PAIR];
+            int oid0[NP2_PAIR], oid1[NP2_PAIR];
+#pragma unroll
+            for (int i = 0; i < NP2_PAIR; ++i) {
+                const int j = j0 + i;
+                oh[i] = make_float4(0.f, 0.f, 0.f, 0.f); ometa[i] = make_int2(0, -1); oid0[i] = oid1[i] = 0;
+                if (old[j] >= 0 && slot[threadIdx.x * NP2_ITEMS + j].count > 0) {
+                    oh[i] = prev.hdr[old[j]];
+                    ometa[i] = prev.meta[old[j]];
+                    oid0[i] = prev.cid[2 * old[j]];
+                    oid1[i] = prev.cid[2 * old[j] + 1];
+                }
             }
-            if (pos < w.cap_manifolds) {
-                const bool two = sl.count > 1;
-                cur.key[pos] = make_uint2(ua, ub);
-                cur.body[pos] = pr[j];
-                cur.hdr[pos] = make_float4(sl.dx, sl.dy, friction, restitution);
-                cur.meta[pos] = make_int2(sl.count, color);
-                cur.geo[2 * pos] = make_float4(sl.p0x, sl.p0y, sl.d0, stamp);
-                cur.geo[2 * pos + 1] = make_float4(sl.p1x, sl.p1y, sl.d1, two ? stamp : 0.0f);
-                cur.imp[2 * pos] = make_float4(0.0f, lam_n0, 0.0f, lam_t0);
-                cur.imp[2 * pos + 1] = make_float4(0.0f, two ? lam_n1 : 0.0f, 0.0f, two ? lam_t1 : 0.0f);
-                cur.cid[2 * pos] = sl.id0;
-                cur.cid[2 * pos + 1] = sl.id1;
+#pragma unroll
+            for (int i = 0; i < NP2_PAIR; ++i) {
+                const int j = j0 + i;
+                if (pr[j].x < 0) continue;
+                const NpSlot &sl = slot[threadIdx.x * NP2_ITEMS + j];
+                if (sl.count <= 0) continue;
+                float friction, restitution;
+                float lam_n0 = 0.0f, lam_t0 = 0.0f, lam_n1 = 0.0f, lam_t1 = 0.0f;
+                int color = -1;
+                if (old[j] >= 0) {
+                    friction = oh[i].z;
+                    restitution = oh[i].w;
+                    color = ometa[i].y;                                 // keep last step's colour
+                    int o0 = -1, o1 = -1;
+                    if (ometa[i].x > 0 && sl.id0 == oid0[i]) o0 = 0; else if (ometa[i].x > 1 && sl.id0 == oid1[i]) o0 = 1;
+                    if (sl.count > 1) { if (ometa[i].x > 0 && sl.id1 == oid0[i]) o1 = 0; else if (ometa[i].x > 1 && sl.id1 == oid1[i]) o1 = 1; }
+                    // level 5: the impulses (the two loads of an entry are independent of each other)
+                    float4 oi0 = make_float4(0.f, 0.f, 0.f, 0.f), oi1 = oi0;
+                    if (o0 >= 0) oi0 = prev.imp[2 * old[j] + o0];
+                    if (o1 >= 0) oi1 = prev.imp[2 * old[j] + o1];
+                    if (o0 >= 0) { lam_n0 = oi0.y; lam_t0 = oi0.w; }
+                    if (o1 >= 0) { lam_n1 = oi1.y; lam_t1 = oi1.w; }
+                } else {                                                // new entry: src/world.c:395-404
+                    const ShapeDev *s1 = &w.shapes[w.shape[pr[j].x].x], *s2 = &w.shapes[w.shape[pr[j].y].x];
+                    friction = 0.5f * (s1->friction + s2->friction);
+                    restitution = pin_fminf(s1->restitution, s2->restitution);
+                    if (friction < 0.0f) friction = 0.0f;
+                    if (restitution < 0.0f) restitution = 0.0f;
+                }
+                if (pos < w.cap_manifolds) {
+                    const bool two = sl.count > 1;
+                    cur.key[pos] = make_uint2(ua[j], ub[j]);
+                    cur.body[pos] = pr[j];
+                    cur.hdr[pos] = make_float4(sl.dx, sl.dy, friction, restitution);
+                    cur.meta[pos] = make_int2(sl.count, color);
+                    cur.geo[2 * pos] = make_float4(sl.p0x, sl.p0y, sl.d0, stamp);
+                    cur.geo[2 * pos + 1] = make_float4(sl.p1x, sl.p1y, sl.d1, two ? stamp : 0.0f);
+                    cur.imp[2 * pos] = make_float4(0.0f, lam_n0, 0.0f, lam_t0);
+                    cur.imp[2 * pos + 1] = make_float4(0.0f, two ? lam_n1 : 0.0f, 0.0f, two ? lam_t1 : 0.0f);
+                    cur.cid[2 * pos] = sl.id0;
+                    cur.cid[2 * pos + 1] = sl.id1;
+                }
+                ++pos;
             }
-            ++pos;
         }
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) q += __shfl_xor_sync(0xffffffffu, q, d);

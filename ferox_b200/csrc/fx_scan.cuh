@@ -73,6 +73,12 @@ FX_D unsigned int claim_tile(unsigned int *ticket) {
 // hundreds of tiles in flight the prefix frontier advances one window per L2 round trip, so the
 // window width sets the speed of every ordered sweep ([measured] narrow phase, 4,216 tiles of the
 // 65k-body config: 1 thread 186 us, one warp 177 us; see DESIGN.md for the block-wide figure).
+// A tile may publish its aggregate as soon as it knows it and do other work before it looks back (the tiles behind it
+// then never wait for that work); tile_exclusive_prefix stores the same word again, which is harmless.
+FX_D void tile_publish_aggregate(unsigned long long *status, unsigned int tile, unsigned int tile_total) {
+    if (tile > 0 && threadIdx.x == 0) st_status(&status[tile], FX_TILE_AGG | (unsigned long long) tile_total);
+}
+
 FX_D unsigned int tile_exclusive_prefix(unsigned long long *status, unsigned int tile,
                                         unsigned int tile_total) {
     __shared__ unsigned long long s_part[32];
