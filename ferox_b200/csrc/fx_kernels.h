@@ -9,6 +9,7 @@ struct FxLaunchCtx {
     int max_blocks;                 // grid cap for grid-stride kernels (multiple of the SM count)
     int coop_blocks;                // co-resident grid of the cooperative solver kernel
     int num_sms;
+    int solve_blocks_cap;           // > 0: the coloured solver takes at most this many blocks (FEROX_SOLVE_BLOCKS, read per world: tests)
     unsigned long long *status[4];  // 0 body prepass, 1 pair emission, 2 narrow phase, 3 carry-over
     size_t status_words[4];
     unsigned int *tickets;          // [16]

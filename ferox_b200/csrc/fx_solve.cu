@@ -462,6 +462,11 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     // the start of a phase so that DRAM keeps streaming under the gather, the arithmetic and the barrier -- at 1 M bodies,
     // where a colour's records are ~40 MB and come from DRAM in every sweep: bit-identical, solve 1.837 -> 2.003 ms.  Nothing
     // is saturated there (DRAM 31 %, L2 34 %); two colours' records do not stay in L2 next to the velocities)
+    // ([measured] sweeping TWO manifolds per thread side by side in the lean builds -- cp.async lands both records in the
+    // thread's own shared-memory slots, both velocity pairs are gathered at once, then the two updates run; bit-identical,
+    // tests/test_gpu_large.py -- at 1 M circles, where a thread has one to three manifolds per phase: solve 1.757 -> 1.768 ms.
+    // A launch list of the strip step (profiles/r02_launches_config5_n1.csv), which launches the stages separately, shows
+    // where a 1 M-body solve goes: set-up + colouring + records + warm start 0.49 ms, ten sweeps 0.107 ms each, write-back 0.065)
     // ([measured] fetching a thread's NEXT record between the halves of a split grid barrier -- grid.barrier_arrive(), loads,
     // grid.barrier_wait() -- was bit-identical and no faster either, solve 0.297 -> 0.309 ms at 65k bodies: the phase is
     // bound by the barrier and the velocity gather that can only start behind it, not by the record fetch)
@@ -1187,8 +1192,7 @@ int fx_solve_colored_blocks(const FxLaunchCtx &cx, long long work_hint) {
     if (k < 1) k = 1;
     if (k > per_sm) k = per_sm;
     int blocks = (int) (k * cx.num_sms);
-    static const int force_blocks = [] { const char *e = std::getenv("FEROX_SOLVE_BLOCKS"); return e ? std::atoi(e) : 0; }();   // dev knob
-    if (force_blocks > 0 && force_blocks <= blocks) blocks = force_blocks;
+    if (cx.solve_blocks_cap > 0 && cx.solve_blocks_cap <= blocks) blocks = cx.solve_blocks_cap;    // dev / test knob
     if (work_hint <= 2048) blocks = (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK) < 1 ? 1 : (int) ((work_hint + SV_BLOCK - 1) / SV_BLOCK);
     return blocks;
 }

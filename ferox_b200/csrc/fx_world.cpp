@@ -127,6 +127,7 @@ static bool world_device_init(frWorld *w) {
     w->cx.max_blocks = sms * 8;
     w->cx.num_sms = sms;
     w->cx.coop_blocks = fx_query_coop_blocks(w->device);
+    { const char *e = std::getenv("FEROX_SOLVE_BLOCKS"); w->cx.solve_blocks_cap = e ? std::atoi(e) : 0; }
     fx_init_kernel_attributes();     // function attributes are per device
     bool ok = fx_cuda_ok(cudaMalloc((void **) &w->d_snapshot, sizeof(StepCountersDev)), "cudaMalloc");
     ok = fx_cuda_ok(cudaMallocHost((void **) &w->h_snapshot, sizeof(StepCountersDev)), "cudaMallocHost") && ok;

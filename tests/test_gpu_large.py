@@ -134,6 +134,27 @@ def test_forced_large_variants_colored_mode_same_bits_as_small_variants(gpu, mon
     assert out[0][2]["colors"] == out[1][2]["colors"] and out[0][2]["manifolds"] > 6000
 
 
+@pytest.mark.parametrize("blocks", ["1", "3"])
+def test_lean_records_with_several_manifolds_per_thread_same_bits(gpu, monkeypatch, blocks):
+    """Large grid-solved worlds sweep LEAN records (normal + lever arms; tangent and unit perpendiculars recomputed every
+    sweep), and only 1 M-body worlds give a thread more than one manifold per colour phase.  Squeezing the grid to 1 / 3
+    blocks (FEROX_SOLVE_BLOCKS, read per world) gives every thread of a 6,000-body pile up to four, and 300 steps must end
+    in the bits of the default small-world build (full records, one manifold per thread), manifold for manifold."""
+    L = gpu
+    out = []
+    for env in ({"FEROX_FORCE_LARGE": "0", "FEROX_SOLVE_BLOCKS": "0"}, {"FEROX_FORCE_LARGE": "1", "FEROX_SOLVE_BLOCKS": blocks}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        sc = make_world(L, scenes.mixed_pile(6000, width=150.0), fb.SOLVER_COLORED)
+        L.frxStepWorldN(sc.world, DT, 300)
+        fb.check_error(L)
+        out.append((fb.body_states(L, sc.world), fb.manifolds(L, sc.world), fb.step_counters(L, sc.world)))
+        sc.release()
+    assert_states_equal(out[0][0], out[1][0], "lean records, squeezed grid vs default")
+    assert_caches_equal(out[0][1], out[1][1], "manifolds", timestamps=True)
+    assert out[0][2]["colors"] == out[1][2]["colors"] and out[0][2]["manifolds"] > 6000
+
+
 # ------------------------------------------------------------------------------------------------
 # full-size worlds against the oracle
 # ------------------------------------------------------------------------------------------------
