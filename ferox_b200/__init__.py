@@ -84,6 +84,7 @@ EXT_PROTOTYPES = {
     "frxGetGraphReplays": (C.c_longlong, [P]),
     "frxGetWorldSolverKernel": (I, [P]),
     "frxGetColorHistogram": (I, [P, i32p]),
+    "frxGetSolveTrace": (I, [P, C.POINTER(C.c_ulonglong), I]),
     "frxProfilerRange": (None, [I]),
     "frxTimedSteps": (I, [P, F, I, I, f32p]),
 }

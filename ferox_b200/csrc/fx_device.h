@@ -81,6 +81,7 @@ struct ManifoldSet {
 
 // Solver constraint records, colour-major, written once per step by the prepare phase and streamed
 // by every Gauss-Seidel sweep.
+#define FX_TRACE_SLOTS 32     // 0 start, 1 body state, 2 colours validated, 3 rounds done, 4 counted, 5 ordered, 6 records + warm start, 7.. after sweep i, 30 write-back, 31 rounds
 struct SolverSet {
     int2 *body;      // {idxA, idxB}
     float4 *nt;      // {n.x, n.y, t.x, t.y}                            (full records)
@@ -179,6 +180,7 @@ struct DevWorld {
     unsigned int *winner;                // colouring: per-body claim, [2][n] (alternating by round)
     int2 *cbody;                         // per manifold: the bodies that constrain its colour (-1: none)
     unsigned int *color_scratch;         // [4][FX_MAX_COLORS]: counts, fill cursors, per-round remaining, flags
+    unsigned long long *solve_trace;     // FEROX_SOLVE_TRACE=1: [FX_TRACE_SLOTS] globaltimer stamps of k_solve_colored's stages (else nullptr)
     // single-pass ordered compaction (decoupled look-back)
     StepCountersDev *ctr;                // current step
     unsigned int *prev_count;            // [0] number of entries in the prev manifold set, [1] colours used by the last solve

@@ -291,6 +291,9 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     const unsigned int vtid = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u);
     unsigned int *color_cnt = w.color_scratch, *color_fill = w.color_scratch + FX_MAX_COLORS,
                  *color_rem = w.color_scratch + 2 * FX_MAX_COLORS;
+    // opt-in stage trace (FEROX_SOLVE_TRACE=1, frxGetSolveTrace): one thread stamps the global timer behind the barriers
+#define SV_TRACE(slot) do { if (w.solve_trace != nullptr && tid == 0) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); w.solve_trace[slot] = t_; } } while (0)
+    SV_TRACE(0);
 
     if (phases & SV_SETUP) {
     // ---- phase 0: per-body colouring state.  Manifolds that persist from the previous step arrive
@@ -306,6 +309,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     }
     for (unsigned int i = tid; i < 4 * FX_MAX_COLORS; i += nth) w.color_scratch[i] = 0u;
     grid.sync();
+    SV_TRACE(1);
     // Colours are inherited from step to step, and contacts come and go: without care the palette creeps up (14
     // colours for a 1 M-circle pile whose bodies touch at most 7 others).  Every step the manifolds holding the
     // top two colours of the previous solve go back into the rounds and take the lowest colour that is free
@@ -332,6 +336,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
         }
     }
     grid.sync();
+    SV_TRACE(2);
     if (*reinterpret_cast<volatile unsigned int *>(dup_flag)) {     // rare (a body changed type or flags): grid-uniform
         for (unsigned int m = tid; m < M; m += nth) {
             int2 meta = man.meta[m];
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     }
     for (unsigned int round = 0; round <= 64u; ++round) {
         grid.sync();
-        if (round > 0u && (color_rem[round - 1u] == 0u || round == 64u)) { if (tid == 0) w.ctr->uncolored = round; break; }
+        if (round > 0u && (color_rem[round - 1u] == 0u || round == 64u)) { if (tid == 0) w.ctr->uncolored = round; SV_TRACE(3); break; }
         const unsigned int *win = w.winner + (size_t) (round & 1u) * (size_t) w.n;
         unsigned int *next = w.winner + (size_t) ((round + 1u) & 1u) * (size_t) w.n;
         unsigned int left = 0u;
@@ -398,6 +403,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
     __syncthreads();
     if (threadIdx.x < FX_MAX_COLORS && s_hist[threadIdx.x]) atomicAdd(&color_cnt[threadIdx.x], s_hist[threadIdx.x]);
     grid.sync();
+    SV_TRACE(4);
     if (threadIdx.x == 0) {
         unsigned int run = 0u, nc = 0u;
         for (int c = 0; c < FX_MAX_COLORS; ++c) {
@@ -424,26 +430,30 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
         unsigned int pos = 0u;
         if (col >= 0 && before == 0u) pos = atomicAdd(&color_fill[col], (unsigned int) __popc(peers));
         pos = __shfl_sync(0xffffffffu, pos, __ffs(peers) - 1);
-        if (col >= 0) w.order[s_off[col] + pos + before] = m;
+        // The solver record of manifold m is built HERE, in manifold order, and written to its slot: everything in it
+        // depends on positions only.  The manifold arrays are read densely (whole sectors, every byte used); built per
+        // colour through order[] instead, a warp read every tenth manifold of a stretch and half of every sector it
+        // touched was another colour's ([measured] 1 M circles: ordering 49 us + ten record/warm-start phases 294 us).
+        if (col >= 0) {
+            const unsigned int slot = s_off[col] + pos + before;
+            w.order[slot] = m;
+            const int2 b = man.body[m];
+            build_record<LEAN>(w, man, m, slot, w.vel[b.x].w, w.vel[b.y].w, inv_dt);
+        }
     }
     grid.sync();
+    SV_TRACE(5);
 
     const VelArray gvel = { w.vel, 0 };
-    if (phases & SV_RECORDS_ONLY) {
-        // the records depend on positions only: one pass over all slots, no barrier; the cluster kernel warm-starts
-        for (unsigned int s = tid; s < M; s += nth) {
-            const unsigned int m = w.order[s];
-            const int2 b = man.body[m];
-            build_record<LEAN>(w, man, m, s, w.vel[b.x].w, w.vel[b.y].w, inv_dt);
-        }
-        return;
-    }
-    // ---- phase 3: solver records + warm start, one colour at a time
+    if (phases & SV_RECORDS_ONLY) return;          // the cluster kernel warm-starts from the records
+    // ---- phase 3: warm start from the records, one colour at a time
     for (unsigned int c = 0; c < s_ncolors; ++c) {
         if (s_off[c] == s_off[c + 1]) continue;      // an emptied colour: nothing to do, no barrier (uniform)
-        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) prepare_and_warm_start<LEAN>(w, man, w.order[s], s, gvel, inv_dt);
+        for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth)
+            warm_start_apply(load_warm_record<LEAN>(w, s, w.sol.body[s], w.sol.count_src[s]), gvel);
         grid.sync();
     }
+    SV_TRACE(6);
     } else {
         // a later launch of the same step: the colour layout is in global memory
         if (threadIdx.x <= FX_MAX_COLORS) s_off[threadIdx.x] = w.color_off[threadIdx.x];
@@ -476,6 +486,7 @@ __global__ void __launch_bounds__(SV_BLOCK, MINB) k_solve_colored(DevWorld w, in
             if (s_off[c] == s_off[c + 1]) continue;
             for (unsigned int s = s_off[c] + vtid; s < s_off[c + 1]; s += nth) sweep_one<LEAN>(w, s, gvel2);
             grid.sync();
+            if (c + 1 == ncolors && it < 23) SV_TRACE(7 + it);
         }
     // ---- phase 5: write the impulses and effective masses back to the cache
     if (phases & SV_WRITEBACK)

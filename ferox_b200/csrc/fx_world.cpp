@@ -138,6 +138,11 @@ static bool world_device_init(frWorld *w) {
     ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.cur_flip, sizeof(int)), "cudaMalloc") && ok;
     ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.color_off, (FX_MAX_COLORS + 1) * sizeof(unsigned int)), "cudaMalloc") && ok;
     ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.color_scratch, 4 * FX_MAX_COLORS * sizeof(unsigned int)), "cudaMalloc") && ok;
+    w->dw.solve_trace = nullptr;
+    if (const char *e = std::getenv("FEROX_SOLVE_TRACE")) if (std::atoi(e) > 0) {
+        ok = fx_cuda_ok(cudaMalloc((void **) &w->dw.solve_trace, FX_TRACE_SLOTS * sizeof(unsigned long long)), "cudaMalloc") && ok;
+        if (w->dw.solve_trace) cudaMemset(w->dw.solve_trace, 0, FX_TRACE_SLOTS * sizeof(unsigned long long));
+    }
     ok = fx_cuda_ok(cudaMalloc((void **) &w->d_scal, sizeof(StepScalars)), "cudaMalloc") && ok;
     if (!ok) return false;
     w->dw.scal = w->d_scal;
@@ -184,7 +189,7 @@ static void world_free_device(frWorld *w) {
     cudaFree(d.sol.body); cudaFree(d.sol.nt); cudaFree(d.sol.n); cudaFree(d.sol.mat); cudaFree(d.sol.count_src);
     cudaFree(d.sol.r); cudaFree(d.sol.u); cudaFree(d.sol.k); cudaFree(d.sol.lam);
     cudaFree(d.order); cudaFree(d.color_off); cudaFree(d.body_mask); cudaFree(d.body_dup); cudaFree(d.winner); cudaFree(d.cbody);
-    cudaFree(d.color_scratch); cudaFree(d.ctr); cudaFree(d.prev_count); cudaFree(d.cur_flip); cudaFree(w->d_scal);
+    cudaFree(d.solve_trace); cudaFree(d.color_scratch); cudaFree(d.ctr); cudaFree(d.prev_count); cudaFree(d.cur_flip); cudaFree(w->d_scal);
     cudaFree(w->cx.zero_base);
     cudaFree(w->lex.keys[0]); cudaFree(w->lex.keys[1]); cudaFree(w->lex.vals[0]); cudaFree(w->lex.vals[1]);
     cudaFree(w->lex.tmp); cudaFree(w->lex.zero_base);
@@ -1090,6 +1095,18 @@ extern "C" int frxGetColorHistogram(frWorld *w, int *out64) {
         out64[c] = (int) (off[c + 1] - off[c]);
         if (out64[c] > 0) n = c + 1;
     }
+    return n;
+}
+// FEROX_SOLVE_TRACE=1 (read when the world is created): global-timer stamps (ns) the coloured solver left behind its
+// stages in the LAST step -- [0] start, [1] body state cleared, [2] inherited colours validated, [3] colouring rounds
+// done, [4] colours counted, [5] manifolds ordered by colour, [6] records built + warm start, [7 + i] sweep i done.
+// Returns the number of slots written to `out` (0: tracing is off).
+extern "C" int frxGetSolveTrace(frWorld *w, unsigned long long *out, int n) {
+    if (!w || !w->device_ok || !out || !w->dw.solve_trace) return 0;
+    if (n > FX_TRACE_SLOTS) n = FX_TRACE_SLOTS;
+    cudaSetDevice(w->device);
+    cudaMemcpyAsync(out, w->dw.solve_trace, (size_t) n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, w->stream);
+    if (!fx_cuda_ok(cudaStreamSynchronize(w->stream), "solve trace")) return 0;
     return n;
 }
 extern "C" int frxGetWorldSolverKernel(const frWorld *w) {

@@ -370,6 +370,11 @@ long long frxGetGraphReplays(const frWorld *w);
 int frxGetWorldSolverKernel(const frWorld *w);
 /* manifolds per colour of the last production-mode step: out[c] for c < 64; returns the number of colours */
 int frxGetColorHistogram(frWorld *w, int *out64);
+/* FEROX_SOLVE_TRACE=1 in the environment when the world is created: global-timer stamps (ns) of the coloured solver's
+   stages in the last step -- [0] start, [1] body state cleared, [2] inherited colours validated, [3] colouring rounds
+   done, [4] colours counted, [5] manifolds ordered by colour, [6] records built + warm start, [7 + i] sweep i done.
+   Returns the slots written (0: tracing is off). */
+int frxGetSolveTrace(frWorld *w, unsigned long long *out, int n);
 /* cudaProfilerStart (1) / cudaProfilerStop (0): lets `ncu --profile-from-start off` capture a span */
 void frxProfilerRange(int start);
 /* n frStepWorld calls, each bracketed by its own CUDA-event pair on the world's stream; with flushL2
