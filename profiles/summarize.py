@@ -9,7 +9,7 @@ launch_csv, rep, tag = sys.argv[1:4]
 lines = [l for l in open(launch_csv) if not l.startswith("==")]
 tot, cnt = collections.OrderedDict(), collections.Counter()
 for row in csv.DictReader(lines):
-    name = row["Kernel Name"].split("(")[0]
+    name = row["Kernel Name"].split("(")[0].replace(", ", ";")      # template arguments: no commas inside a CSV field
     try:
         v = float(row["Metric Value"].replace(",", ""))
     except ValueError:
@@ -38,6 +38,6 @@ hdr, units = rows[0], rows[1]
 idx = {h: i for i, h in enumerate(hdr)}
 out = ["kernel," + ",".join(want), "unit," + ",".join(units[idx[h]] if h in idx else "" for h in want)]
 for r in rows[2:]:
-    out.append(r[idx["Kernel Name"]].split("(")[0] + "," + ",".join(r[idx[h]].replace(",", "") if h in idx else "" for h in want))
+    out.append(r[idx["Kernel Name"]].split("(")[0].replace(", ", ";") + "," + ",".join(r[idx[h]].replace(",", "") if h in idx else "" for h in want))
 open("profiles/%s_top_kernels_ncu.csv" % tag, "w").write("\n".join(out) + "\n")
 print("\n".join(out))
