@@ -105,6 +105,7 @@ struct frWorld_ {
     bool extent_unknown = false;     // a setter moved a body: launch every sort pass until a step has re-measured the key width
     long long extent_mark_step = 0;  // w->steps when that happened
     long long snapshot_step = -1;    // index of the step the pending / last snapshot belongs to
+    long long snapshot_read_step = 0;  // w->steps when a snapshot was last read (the host never runs further ahead than FX_MAX_RUN_AHEAD steps)
     StepScalars *d_scal = nullptr;   // device block behind DevWorld::scal
     StepScalars scal_dev{};          // what that block holds
     bool scal_valid = false;

@@ -359,7 +359,7 @@ void fx_world_mark(frWorld *w, unsigned bits) {
 // no change of the graph key).
 static void read_snapshot(frWorld *w, bool wait);
 void fx_world_mark_body(frWorld *w, int index, unsigned bits) {
-    if ((bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) && w->snapshot_pending) read_snapshot(w, false);   // (a poll, never a wait)
+    if ((bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) && w->snapshot_pending) read_snapshot(w, false);   // (a poll; it waits only when the host is FX_MAX_RUN_AHEAD steps ahead of the device)
     if ((bits & (FX_DIRTY_POSROT | FX_DIRTY_AABB | FX_DIRTY_SHAPE)) && !w->extent_unknown && w->last.key_bits != 0u &&
         index >= 0 && index < (int) w->bodies.size() && w->cell > 0.0f && !w->snapshot_pending) {
         const float4 a = w->h.aabb[index];
@@ -796,11 +796,21 @@ static void fill_dev_params(frWorld *w, float dt) {
     d.gorder = w->d_gorder;
 }
 
+// The step is sized from the counters of the last snapshot the host has SEEN (sort passes for its key width plus one
+// digit, kernel variants for its manifold count).  A caller that enqueues steps faster than the device runs them (a
+// loop of frStepWorld, frxStepWorldN) would see none until the queue drains -- the one event always belongs to the newest
+// step -- and a world whose extent explodes meanwhile would have every remaining step of the batch refused for want of
+// sort passes ([measured] the config-3 column once it bursts: bench.py `config3`).  So the host never runs more than
+// FX_MAX_RUN_AHEAD steps past the last snapshot it read: then it waits for the device once (a bubble of one step's
+// launch latency per 16 steps).
+#define FX_MAX_RUN_AHEAD 16
 static void read_snapshot(frWorld *w, bool wait) {
     if (!w->snapshot_pending) return;
+    if (!wait && w->steps - w->snapshot_read_step >= FX_MAX_RUN_AHEAD) wait = true;
     if (wait) cudaEventSynchronize(w->snapshot_ready);
     else if (cudaEventQuery(w->snapshot_ready) != cudaSuccess) return;
     w->snapshot_pending = false;
+    w->snapshot_read_step = w->steps;
     w->last = *w->h_snapshot;
     w->manifold_hint = w->last.n_manifolds;
     // bit 128 (a body outside its strip, static ownership) is a condition the caller reads from the counters, not lost work
