@@ -476,47 +476,33 @@ __device__ __forceinline__ bool pair_ok(unsigned int a, unsigned int b) {
     return (u & ENT_MASS) && (u & ENT_X0) && (u & ENT_Y0);
 }
 
+// ([measured] round 2: staging the tile and the 128 entries behind it in shared memory, so that both walks read shared
+// memory, left the small-world build where it was (20.3 vs 20.5 us at 65k bodies) and made the large one SLOWER -- 107 vs
+// 87 us at 2.4 M entries, 56 M warp instructions instead of 36 M: the runs are two or three entries long and L1 already
+// serves the second walk.  Removed.)
 // ITEMS consecutive entries per thread: large worlds take 4 (tiles of 1,024 entries: the look-back chain is 4x
 // shorter), small ones 1 (more blocks in flight matter more there).
-// Every entry walks forward through the rest of its cell run twice (count, then emit).  The tile and the PAIR_HALO
-// entries behind it are staged in shared memory by one coalesced load, so both walks are shared-memory reads; a
-// run that leaves the staged window (> PAIR_HALO bodies in one cell) and wide keys read global memory as before.
-#define PAIR_HALO 128
 template <int ITEMS>
 __global__ void __launch_bounds__(BP_BLOCK) k_emit_pairs(DevWorld w, unsigned long long *status, unsigned int *ticket) {
-    constexpr unsigned int TILE = BP_BLOCK * ITEMS, WINDOW = TILE + PAIR_HALO;
-    __shared__ unsigned int s_k[WINDOW], s_v[WINDOW];
     const unsigned int n = w.ctr->n_entries;
     const unsigned int sel = w.ctr->sort_passes & 1u;
     const unsigned int *keys = w.keys[sel], *vals = w.vals[sel];
     const unsigned int *khi = w.ctr->key_bits > 32u ? w.keys_hi[sel] : nullptr;      // wide keys: a run shares both words
-    const bool staged = khi == nullptr;
-    const unsigned int ntiles = (n + TILE - 1) / TILE;
+    const unsigned int tile_size = BP_BLOCK * ITEMS;
+    const unsigned int ntiles = (n + tile_size - 1) / tile_size;
     if (ntiles == 0 && blockIdx.x == 0 && threadIdx.x == 0) w.ctr->n_cand = 0;
     for (;;) {
-        unsigned int tile = claim_tile(ticket);          // (its barriers also fence the previous tile's reads of s_k / s_v)
+        unsigned int tile = claim_tile(ticket);
         if (tile >= ntiles) return;
-        const unsigned int tbase = tile * TILE;
-        if (staged) {
-            for (unsigned int i = threadIdx.x; i < WINDOW; i += BP_BLOCK) {
-                const unsigned int e = tbase + i;
-                s_k[i] = e < n ? keys[e] : 0u;
-                s_v[i] = e < n ? vals[e] : 0u;
-            }
-            __syncthreads();
-        }
-        // entry f (>= tbase) of the sorted list: from the staged window when it is there
-        auto key_at = [&](unsigned int f) { const unsigned int i = f - tbase; return (staged && i < WINDOW) ? s_k[i] : keys[f]; };
-        auto val_at = [&](unsigned int f) { const unsigned int i = f - tbase; return (staged && i < WINDOW) ? s_v[i] : vals[f]; };
-        const unsigned int first = tbase + threadIdx.x * ITEMS;
+        const unsigned int first = tile * tile_size + threadIdx.x * ITEMS;
         unsigned int cnt[ITEMS], sum = 0u;
 #pragma unroll
         for (int j = 0; j < ITEMS; ++j) {
             const unsigned int e = first + j;
             cnt[j] = 0u;
             if (e < n) {
-                const unsigned int k = key_at(e), v = val_at(e), kh = khi ? khi[e] : 0u;
-                for (unsigned int f = e + 1; f < n && key_at(f) == k && (!khi || khi[f] == kh); ++f) cnt[j] += pair_ok(v, val_at(f)) ? 1u : 0u;
+                const unsigned int k = keys[e], v = vals[e], kh = khi ? khi[e] : 0u;
+                for (unsigned int f = e + 1; f < n && keys[f] == k && (!khi || khi[f] == kh); ++f) cnt[j] += pair_ok(v, vals[f]) ? 1u : 0u;
             }
             sum += cnt[j];
         }
@@ -528,9 +514,9 @@ __global__ void __launch_bounds__(BP_BLOCK) k_emit_pairs(DevWorld w, unsigned lo
         for (int j = 0; j < ITEMS; ++j) {
             if (!cnt[j]) continue;
             const unsigned int e = first + j;
-            const unsigned int k = key_at(e), v = val_at(e), kh = khi ? khi[e] : 0u;
-            for (unsigned int f = e + 1; f < n && key_at(f) == k && (!khi || khi[f] == kh); ++f) {
-                unsigned int vf = val_at(f);
+            const unsigned int k = keys[e], v = vals[e], kh = khi ? khi[e] : 0u;
+            for (unsigned int f = e + 1; f < n && keys[f] == k && (!khi || khi[f] == kh); ++f) {
+                unsigned int vf = vals[f];
                 if (pair_ok(v, vf)) {
                     // entries of one cell are in ascending body order (stable sort of an ascending
                     // emission), so ENT_BODY(v) < ENT_BODY(vf): the reference's i < j (world.c:333)
