@@ -347,10 +347,12 @@ def sub_config3(L, dt, bodies=1048576):
                        "wall removed at t = 0, static floor 16,384 units wide, cell 2.0, dt 1/60; the 600 steps of the collapse are the "
                        "timed region (per-step working set > 2 GB, far larger than the 126 MB L2)" % (bodies, (bodies + 511) // 512),
            "bodies": n, "steps": 600}
-    ms_all, marks, errors = [], {}, []
+    ms_all, marks, errors, calm = [], {}, [], None
     for chunk in range(6):
         ms, stage, ctr, launches = timed_world_steps(L, sc.world, dt, 100, False)
         ms_all.append(ms)
+        if not ctr["overflow"] and not L.frxGetLastError():
+            calm = (ctr, stage, "steps %d-%d" % (100 * chunk + 1, 100 * (chunk + 1)))     # rooflines: the last chunk in which no step was refused
         marks["step_%d" % (100 * (chunk + 1))] = {"ms_per_step": float(ms.mean()), "counters": {k: ctr[k] for k in ("cellEntries", "candidates", "manifolds", "contacts", "colors", "overflow")},
                                                   "stage_ms_per_step": stage}
         if L.frxGetLastError():                      # reported, then the run goes on: the next step re-measures and recovers
@@ -372,9 +374,10 @@ def sub_config3(L, dt, bodies=1048576):
                         "telescopes into the floor in free fall and bursts later (oracle beside the GPU, bit for bit on a 16-column slice: "
                         "tests/test_gpu_large.py::test_config3_column_recipe_overruns_the_reference_solver_too); steady-state 1 M-body "
                         "figures: config3_shallow",
-                "roofline": solver_roofline(ctr, stage["solve"], "k_solve_colored"),
-                "roofline_narrowphase": narrow_roofline(ctr, stage["narrowphase"]),
-                "roofline_broadphase": broad_roofline(n, ctr, stage["broadphase"])})
+                "roofline_at": calm[2] if calm else None,
+                "roofline": solver_roofline(calm[0], calm[1]["solve"], "k_solve_colored") if calm else None,
+                "roofline_narrowphase": narrow_roofline(calm[0], calm[1]["narrowphase"]) if calm else None,
+                "roofline_broadphase": broad_roofline(n, calm[0], calm[1]["broadphase"]) if calm else None})
     L.frxClearLastError()
     sc.release()
     return out
