@@ -34,6 +34,21 @@ def test_reference_arm_is_silent_on_other_ranks():
     assert out.returncode == 0 and out.stdout.strip() == ""
 
 
+def test_committed_ncu_captures_feed_roofline_traffic():
+    """bench.py takes `roofline.traffic` (DRAM bytes of one solver launch) from the ncu summaries committed under
+    profiles/: both captures must parse (kernel names with template arguments carry no comma there) and be plausible."""
+    sys.path.insert(0, ROOT)
+    import bench
+    small, src = bench.ncu_traffic("r02_config2_top_kernels_ncu.csv", "k_solve_colored")
+    large, _ = bench.ncu_traffic("r02_config3_top_kernels_ncu.csv", "k_solve_colored")
+    assert src and "r02_config2_top_kernels_ncu.csv" in src
+    assert 5e6 < small < 5e8, small            # 65k bodies: tens of MB, the working set lives in L2
+    assert 5e8 < large < 2e10, large           # 1 M bodies: GBs, the records stream from DRAM in every sweep
+    for name in ("r02_config2_top_kernels_ncu.csv", "r02_config3_top_kernels_ncu.csv"):
+        rows = [l.rstrip("\n").split(",") for l in open(os.path.join(ROOT, "profiles", name))]
+        assert len({len(r) for r in rows}) == 1, "ragged rows in %s: a kernel name contains a comma" % name
+
+
 @pytest.mark.gpu
 def test_b200_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--bodies", "4096", "--steps", "5", "--warmup", "3",
