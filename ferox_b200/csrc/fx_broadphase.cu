@@ -13,8 +13,9 @@
 //                    (cellKey, packedBody) for every covered cell; bodies covering more
 //                    than FX_LARGE_CELLS cells are expanded by a whole block each (e.g. a ground
 //                    plane spanning thousands of cells)
-//   k_sort_hist + k_sort_pass (x passes)  onesweep-style LSD radix sort, 8-bit digits, one kernel
-//                    per digit with chained-scan look-back per digit; stable, deterministic
+//   k_sort_pass (x passes)  onesweep-style LSD radix sort, 8-bit digits (histograms counted by k_emit_entries), one
+//                    kernel per digit: tiles ranked per warp, reordered in shared memory, chained-scan look-back
+//                    per digit, streamed out in digit order; stable, deterministic
 //   k_emit_pairs     per sorted entry: walk the rest of its cell run; a pair is emitted only in its
 //                    canonical cell (the min-corner of the rectangle intersection), which removes
 //                    duplicates without a hash set; ordered append via look-back
